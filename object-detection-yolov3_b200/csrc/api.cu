@@ -1,0 +1,570 @@
+// api.cu - the extern "C" boundary declared in include/yolo3_b200.h.  Every entry point catches
+// y3::Error (and anything else) and converts it into a negative status + message; nothing throws
+// across the ABI.  There is no CPU fallback: without an sm_100 device y3_create fails.
+#include "common.cuh"
+#include "net.cuh"
+#include "postproc.cuh"
+#include "tiles.cuh"
+
+#include <algorithm>
+#include <mutex>
+
+using namespace y3;
+
+static thread_local std::string g_create_error;
+
+#define Y3_API_BEGIN(h)                                                                   \
+    if (!(h)) return Y3_ERR_INVALID;                                                      \
+    try {                                                                                 \
+        if (cudaSetDevice((h)->device) != cudaSuccess) fail(Y3_ERR_CUDA, "cudaSetDevice(%d) failed", (h)->device);
+#define Y3_API_END(h)                                                                     \
+        return Y3_OK;                                                                     \
+    } catch (const Error& e) {                                                            \
+        (h)->last_error = e.msg;                                                          \
+        cudaGetLastError();                                                               \
+        return e.code;                                                                    \
+    } catch (const std::exception& e) {                                                   \
+        (h)->last_error = std::string("internal error: ") + e.what();                     \
+        return Y3_ERR_CUDA;                                                               \
+    } catch (...) {                                                                       \
+        (h)->last_error = "unknown internal error";                                       \
+        return Y3_ERR_CUDA;                                                               \
+    }
+
+namespace {
+
+struct Phase {
+    y3_context* c;
+    cudaEvent_t a, b;
+    float* dst;
+    Phase(y3_context* ctx, float* d) : c(ctx), dst(d) {
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, c->stream);
+    }
+    void stop() {
+        cudaEventRecord(b, c->stream);
+        cudaEventSynchronize(b);
+        float t = 0; cudaEventElapsedTime(&t, a, b);
+        *dst += t;
+    }
+    ~Phase() { cudaEventDestroy(a); cudaEventDestroy(b); }
+};
+
+const void* to_device(y3_context* c, const void* p, y3_mem mem, size_t bytes, DevBuf& stage) {
+    if (mem == Y3_MEM_DEVICE) return p;
+    stage.reserve(bytes);
+    Y3_CUDA(cudaMemcpyAsync(stage.p, p, bytes, cudaMemcpyHostToDevice, c->stream));
+    return stage.p;
+}
+void from_device(y3_context* c, void* dst, y3_mem mem, const void* src, size_t bytes) {
+    if (!bytes) return;
+    Y3_CUDA(cudaMemcpyAsync(dst, src, bytes, mem == Y3_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+}
+PostProc* post_of(y3_context* c) {
+    if (!c->post) c->post = new PostProc(c);
+    return c->post;
+}
+Tiler* tiler_of(y3_context* c) {
+    if (!c->tiler) c->tiler = new Tiler(c);
+    return c->tiler;
+}
+Net* net_of(y3_context* c) {
+    Y3_CHECK(c->net, Y3_ERR_STATE, "this handle was created without a network (img_h == 0)");
+    return c->net;
+}
+size_t dtype_size(int dt) { return dt == Y3_U8 ? 1 : dt == Y3_U16 ? 2 : 4; }
+
+__global__ void k_iou_row(float4 box, const float* __restrict__ boxes, int64_t m, float* __restrict__ out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const float4 b = make_float4(boxes[4 * j], boxes[4 * j + 1], boxes[4 * j + 2], boxes[4 * j + 3]);
+    out[j] = iou_exact(box, box_area_exact(box), b, box_area_exact(b));
+}
+__global__ void k_small_flags(const float* __restrict__ rows, int64_t n, int row_len, float min_size, uint8_t* __restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* r = rows + i * row_len;
+    const float w = __fsub_rn(r[2], r[0]), h = __fsub_rn(r[3], r[1]);
+    flags[i] = (w > min_size && h > min_size) ? 1 : 0;
+}
+__global__ void __launch_bounds__(CMP_BLOCK)
+k_small_scatter(const float* __restrict__ rows, int64_t n, int row_len, const uint8_t* __restrict__ flags,
+                const int* __restrict__ blk, float* __restrict__ out, long long* __restrict__ out_idx) {
+    __shared__ int s_w[CMP_BLOCK / 32];
+    __shared__ long long s_dst[CMP_BLOCK];
+    const int64_t p = (int64_t)blockIdx.x * CMP_BLOCK + threadIdx.x;
+    const bool f = p < n && flags[p];
+    const int rank = block_rank(f, s_w);
+    const long long q = (long long)blk[blockIdx.x] + rank;
+    s_dst[threadIdx.x] = f ? q : -1;
+    if (f && out_idx) out_idx[q] = p;
+    __syncthreads();
+    // copy rows cooperatively: consecutive threads copy consecutive floats
+    const int64_t base = (int64_t)blockIdx.x * CMP_BLOCK;
+    const int64_t cnt = min((int64_t)CMP_BLOCK, n - base);
+    for (int64_t e = threadIdx.x; e < cnt * row_len; e += CMP_BLOCK) {
+        const int r = (int)(e / row_len), k = (int)(e - (int64_t)r * row_len);
+        const long long d = s_dst[r];
+        if (d >= 0) out[d * row_len + k] = rows[(base + r) * row_len + k];
+    }
+}
+// shared by y3_detect / y3_stitch_tiles / y3_infer_tiled
+CandSource dets_source(const float* dets_dev, int64_t n_per_img, int n_img, int nc, bool filter, float min_box, float score_thr) {
+    CandSource s;
+    const int E = 5 + nc;
+    s.box = dets_dev; s.box_stride = E;
+    s.obj = dets_dev + 4; s.obj_stride = E;
+    s.cls = dets_dev + 5; s.cls_stride = E;
+    s.rows_per_image = n_per_img; s.n_images = n_img; s.nc = nc;
+    s.filter_small = filter; s.min_size = min_box; s.score_thr = score_thr;
+    return s;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+int32_t y3_abi_version(void) { return Y3_ABI_VERSION; }
+
+const char* y3_last_error(y3_handle h) { return h ? h->last_error.c_str() : g_create_error.c_str(); }
+
+y3_status y3_create(const y3_config* cfg, y3_handle* out) {
+    if (!cfg || !out) { g_create_error = "y3_create: NULL argument"; return Y3_ERR_INVALID; }
+    *out = nullptr;
+    y3_context* c = nullptr;
+    try {
+        Y3_CHECK(cfg->struct_size == (int32_t)sizeof(y3_config), Y3_ERR_INVALID, "y3_config.struct_size %d != %d (ABI mismatch)",
+                 cfg->struct_size, (int)sizeof(y3_config));
+        int n_dev = 0;
+        cudaError_t e = cudaGetDeviceCount(&n_dev);
+        if (e != cudaSuccess || n_dev == 0) {
+            cudaGetLastError();
+            fail(Y3_ERR_NODEVICE, "no CUDA device available (%s) - libyolo3_b200 has no CPU fallback",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        }
+        Y3_CHECK(cfg->device >= 0 && cfg->device < n_dev, Y3_ERR_INVALID, "device %d outside 0..%d", cfg->device, n_dev - 1);
+        cudaDeviceProp prop;
+        Y3_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+        Y3_CHECK(prop.major == 10, Y3_ERR_NODEVICE, "device %d (%s, sm_%d%d) is not an sm_100 part - this library is B200-only",
+                 cfg->device, prop.name, prop.major, prop.minor);
+        Y3_CUDA(cudaSetDevice(cfg->device));
+        c = new y3_context();
+        c->cfg = *cfg;
+        c->device = cfg->device;
+        c->sm_count = prop.multiProcessorCount;
+        Y3_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        if (cfg->img_h > 0) {
+            c->net = new Net(c);
+            c->net->build();
+            Y3_CUDA(cudaDeviceSynchronize());
+        }
+        *out = c;
+        return Y3_OK;
+    } catch (const Error& e) {
+        g_create_error = e.msg;
+        if (c) y3_destroy(c);
+        cudaGetLastError();
+        return e.code;
+    } catch (...) {
+        g_create_error = "unknown internal error in y3_create";
+        if (c) y3_destroy(c);
+        return Y3_ERR_CUDA;
+    }
+}
+
+void y3_destroy(y3_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    delete h->net;
+    delete h->post;
+    delete h->tiler;
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+y3_status y3_load_weights(y3_handle h, int32_t n, const char* const* names, DLManagedTensor* const* tensors) {
+    Y3_API_BEGIN(h)
+    Y3_CHECK(n >= 0 && (n == 0 || (names && tensors)), Y3_ERR_INVALID, "bad weight list");
+    net_of(h)->load(n, names, tensors);
+    Y3_API_END(h)
+}
+
+int64_t y3_boxes_per_image(y3_handle h) { return (h && h->net) ? h->net->rows_per_image : 0; }
+
+y3_status y3_forward_heads(y3_handle h, const float* in, y3_mem in_mem, int32_t batch, float* fm1, float* fm2, float* fm3,
+                           y3_mem out_mem) {
+    Y3_API_BEGIN(h)
+    Net* net = net_of(h);
+    Y3_CHECK(in && fm1 && fm2 && fm3, Y3_ERR_INVALID, "NULL pointer");
+    Y3_CHECK(batch >= 1 && batch <= net->maxB, Y3_ERR_INVALID, "batch %d outside 1..%d", batch, net->maxB);
+    const size_t in_bytes = (size_t)batch * net->C * net->H * net->W * 4;
+    const float* d_in = static_cast<const float*>(to_device(h, in, in_mem, in_bytes, h->stage_in));
+    net->forward(d_in, batch);
+    float* outs[3] = {fm1, fm2, fm3};
+    for (int s = 0; s < 3; ++s) {
+        const int hw = net->gh[s] * net->gw[s];
+        const size_t bytes = (size_t)batch * net->det_c * hw * 4;
+        float* dst = out_mem == Y3_MEM_DEVICE ? outs[s] : (h->stage_out.reserve(bytes), h->stage_out.as<float>());
+        heads_to_nchw(h, net->head[s], dst, batch, hw, net->det_c, HEAD_PITCH);
+        if (out_mem != Y3_MEM_DEVICE) {
+            from_device(h, outs[s], out_mem, dst, bytes);
+            Y3_CUDA(cudaStreamSynchronize(h->stream));
+        }
+    }
+    Y3_CUDA(cudaStreamSynchronize(h->stream));
+    Y3_API_END(h)
+}
+
+y3_status y3_forward_boxes(y3_handle h, const float* in, y3_mem in_mem, int32_t batch, float* out, y3_mem out_mem) {
+    Y3_API_BEGIN(h)
+    Net* net = net_of(h);
+    Y3_CHECK(in && out, Y3_ERR_INVALID, "NULL pointer");
+    Y3_CHECK(batch >= 1 && batch <= net->maxB, Y3_ERR_INVALID, "batch %d outside 1..%d", batch, net->maxB);
+    const size_t in_bytes = (size_t)batch * net->C * net->H * net->W * 4;
+    const float* d_in = static_cast<const float*>(to_device(h, in, in_mem, in_bytes, h->stage_in));
+    net->forward(d_in, batch);
+    net->decode(batch);
+    from_device(h, out, out_mem, net->boxes.p, (size_t)batch * net->rows_per_image * (5 + net->nc) * 4);
+    Y3_CUDA(cudaStreamSynchronize(h->stream));
+    Y3_API_END(h)
+}
+
+y3_status y3_detect(y3_handle h, const float* in, y3_mem in_mem, int32_t batch, float min_box, float iou_thr, float score_thr,
+                    float* out_boxes, float* out_scores, int32_t* out_labels, int32_t* out_img, int64_t cap, int64_t* n_out) {
+    Y3_API_BEGIN(h)
+    Net* net = net_of(h);
+    Y3_CHECK(in && n_out, Y3_ERR_INVALID, "NULL pointer");
+    Y3_CHECK(batch >= 1 && batch <= net->maxB, Y3_ERR_INVALID, "batch %d outside 1..%d", batch, net->maxB);
+    y3_timings& T = h->timings;
+    T = y3_timings{};
+    Phase total(h, &T.ms_total);
+    const size_t in_bytes = (size_t)batch * net->C * net->H * net->W * 4;
+    const float* d_in;
+    { Phase p(h, &T.ms_h2d); d_in = static_cast<const float*>(to_device(h, in, in_mem, in_bytes, h->stage_in)); p.stop(); }
+    { Phase p(h, &T.ms_conv); net->forward(d_in, batch); p.stop(); }
+    { Phase p(h, &T.ms_decode); net->decode(batch); p.stop(); }
+    NmsResult R;
+    {
+        Phase p(h, &T.ms_nms);
+        R = post_of(h)->run(dets_source(net->boxes.as<float>(), net->rows_per_image, batch, net->nc, true, min_box, score_thr), iou_thr);
+        p.stop();
+    }
+    T.candidates = R.n_cand; T.kept = R.n_kept;
+    *n_out = R.n_kept;
+    Y3_CHECK(R.n_kept <= cap, Y3_ERR_NOSPACE, "output capacity %lld < %lld kept boxes", (long long)cap, (long long)R.n_kept);
+    if (R.n_kept) {
+        Phase p(h, &T.ms_d2h);
+        Y3_CHECK(out_boxes && out_scores && out_labels && out_img, Y3_ERR_INVALID, "NULL output");
+        Y3_CUDA(cudaMemcpyAsync(out_boxes, R.boxes, (size_t)R.n_kept * 16, cudaMemcpyDeviceToHost, h->stream));
+        Y3_CUDA(cudaMemcpyAsync(out_scores, R.scores, (size_t)R.n_kept * 4, cudaMemcpyDeviceToHost, h->stream));
+        Y3_CUDA(cudaMemcpyAsync(out_labels, R.labels, (size_t)R.n_kept * 4, cudaMemcpyDeviceToHost, h->stream));
+        Y3_CUDA(cudaMemcpyAsync(out_img, R.img, (size_t)R.n_kept * 4, cudaMemcpyDeviceToHost, h->stream));
+        p.stop();
+    }
+    total.stop();
+    T.kernels_launched = h->kernels_launched;
+    Y3_API_END(h)
+}
+
+y3_status y3_compute_iou(y3_handle h, const float* box, const float* boxes, int64_t m, float* iou) {
+    Y3_API_BEGIN(h)
+    Y3_CHECK(box && (m == 0 || (boxes && iou)) && m >= 0, Y3_ERR_INVALID, "bad arguments");
+    if (m > 0) {
+        const float* d = static_cast<const float*>(to_device(h, boxes, Y3_MEM_HOST, (size_t)m * 16, h->stage_in));
+        h->stage_out.reserve((size_t)m * 4);
+        k_iou_row<<<ceil_div(m, 256), 256, 0, h->stream>>>(make_float4(box[0], box[1], box[2], box[3]), d, m, h->stage_out.as<float>());
+        Y3_LAUNCHED(h);
+        from_device(h, iou, Y3_MEM_HOST, h->stage_out.p, (size_t)m * 4);
+        Y3_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    Y3_API_END(h)
+}
+
+y3_status y3_filter_small(y3_handle h, const float* rows, int64_t n, int32_t row_len, float min_size, float* out_rows,
+                          int64_t* out_index, int64_t cap, int64_t* n_out) {
+    Y3_API_BEGIN(h)
+    Y3_CHECK(n_out && n >= 0 && row_len >= 4 && (n == 0 || rows), Y3_ERR_INVALID, "bad arguments");
+    *n_out = 0;
+    if (n > 0) {
+        PostProc* P = post_of(h);
+        const float* d = static_cast<const float*>(to_device(h, rows, Y3_MEM_HOST, (size_t)n * row_len * 4, h->stage_in));
+        h->stage_aux.reserve((size_t)n);
+        k_small_flags<<<ceil_div(n, 256), 256, 0, h->stream>>>(d, n, row_len, min_size, h->stage_aux.as<uint8_t>());
+        Y3_LAUNCHED(h);
+        const int64_t k = P->flag_offsets(h->stage_aux.as<uint8_t>(), n);
+        *n_out = k;
+        Y3_CHECK(k <= cap, Y3_ERR_NOSPACE, "output capacity %lld < %lld rows", (long long)cap, (long long)k);
+        if (k > 0) {
+            Y3_CHECK(out_rows, Y3_ERR_INVALID, "NULL output");
+            const size_t idx_off = ((size_t)k * row_len * 4 + 7) & ~size_t(7);
+            h->stage_out.reserve(idx_off + (size_t)k * 8);
+            long long* d_idx = reinterpret_cast<long long*>(h->stage_out.as<unsigned char>() + idx_off);
+            k_small_scatter<<<ceil_div(n, CMP_BLOCK), CMP_BLOCK, 0, h->stream>>>(d, n, row_len, h->stage_aux.as<uint8_t>(),
+                                                                               P->blk.as<int>(), h->stage_out.as<float>(), d_idx);
+            Y3_LAUNCHED(h);
+            from_device(h, out_rows, Y3_MEM_HOST, h->stage_out.p, (size_t)k * row_len * 4);
+            if (out_index) from_device(h, out_index, Y3_MEM_HOST, d_idx, (size_t)k * 8);
+            Y3_CUDA(cudaStreamSynchronize(h->stream));
+        }
+    }
+    Y3_API_END(h)
+}
+
+y3_status y3_single_class_nms(y3_handle h, const float* boxes, const float* scores, int64_t m, float iou_thr, int32_t* keep,
+                              int64_t* n_keep) {
+    Y3_API_BEGIN(h)
+    Y3_CHECK(n_keep && m >= 0 && (m == 0 || (boxes && scores && keep)), Y3_ERR_INVALID, "bad arguments");
+    *n_keep = 0;
+    if (m > 0) {
+        y3_timings& T = h->timings;
+        T = y3_timings{};
+        Phase total(h, &T.ms_total);
+        h->stage_in.reserve((size_t)m * 20);
+        float* d_box = h->stage_in.as<float>();
+        float* d_sc = d_box + 4 * m;
+        { Phase p(h, &T.ms_h2d);
+          Y3_CUDA(cudaMemcpyAsync(d_box, boxes, (size_t)m * 16, cudaMemcpyHostToDevice, h->stream));
+          Y3_CUDA(cudaMemcpyAsync(d_sc, scores, (size_t)m * 4, cudaMemcpyHostToDevice, h->stream));
+          p.stop(); }
+        CandSource s;
+        s.box = d_box; s.box_stride = 4; s.cls = d_sc; s.cls_stride = 1; s.obj = nullptr;
+        s.rows_per_image = m; s.n_images = 1; s.nc = 1; s.raw_scores = true;
+        NmsResult R;
+        { Phase p(h, &T.ms_nms); R = post_of(h)->run(s, iou_thr); p.stop(); }
+        *n_keep = R.n_kept;
+        T.candidates = R.n_cand; T.kept = R.n_kept;
+        { Phase p(h, &T.ms_d2h);
+          from_device(h, keep, Y3_MEM_HOST, R.src_row, (size_t)R.n_kept * 4);
+          p.stop(); }
+        total.stop();
+        T.kernels_launched = h->kernels_launched;
+    }
+    Y3_API_END(h)
+}
+
+y3_status y3_per_class_nms(y3_handle h, const float* boxes, const float* obj, const float* cls, int64_t n, int32_t nc,
+                           float iou_thr, float score_thr, float* out_boxes, float* out_scores, int32_t* out_labels,
+                           int32_t* out_src, int64_t cap, int64_t* n_out) {
+    Y3_API_BEGIN(h)
+    Y3_CHECK(n_out && n >= 0 && nc >= 1 && (n == 0 || (boxes && obj && cls)), Y3_ERR_INVALID, "bad arguments");
+    *n_out = 0;
+    if (n > 0) {
+        y3_timings& T = h->timings;
+        T = y3_timings{};
+        Phase total(h, &T.ms_total);
+        h->stage_in.reserve((size_t)n * (5 + nc) * 4);
+        float* d_box = h->stage_in.as<float>();
+        float* d_obj = d_box + 4 * n;
+        float* d_cls = d_obj + n;
+        { Phase p(h, &T.ms_h2d);
+          Y3_CUDA(cudaMemcpyAsync(d_box, boxes, (size_t)n * 16, cudaMemcpyHostToDevice, h->stream));
+          Y3_CUDA(cudaMemcpyAsync(d_obj, obj, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+          Y3_CUDA(cudaMemcpyAsync(d_cls, cls, (size_t)n * nc * 4, cudaMemcpyHostToDevice, h->stream));
+          p.stop(); }
+        CandSource s;
+        s.box = d_box; s.box_stride = 4; s.obj = d_obj; s.obj_stride = 1; s.cls = d_cls; s.cls_stride = nc;
+        s.rows_per_image = n; s.n_images = 1; s.nc = nc; s.score_thr = score_thr;
+        NmsResult R;
+        { Phase p(h, &T.ms_nms); R = post_of(h)->run(s, iou_thr); p.stop(); }
+        *n_out = R.n_kept;
+        T.candidates = R.n_cand; T.kept = R.n_kept;
+        Y3_CHECK(R.n_kept <= cap, Y3_ERR_NOSPACE, "output capacity %lld < %lld kept boxes", (long long)cap, (long long)R.n_kept);
+        if (R.n_kept) {
+            Phase p(h, &T.ms_d2h);
+            Y3_CHECK(out_boxes && out_scores && out_labels, Y3_ERR_INVALID, "NULL output");
+            from_device(h, out_boxes, Y3_MEM_HOST, R.boxes, (size_t)R.n_kept * 16);
+            from_device(h, out_scores, Y3_MEM_HOST, R.scores, (size_t)R.n_kept * 4);
+            from_device(h, out_labels, Y3_MEM_HOST, R.labels, (size_t)R.n_kept * 4);
+            if (out_src) from_device(h, out_src, Y3_MEM_HOST, R.src_row, (size_t)R.n_kept * 4);
+            p.stop();
+        }
+        total.stop();
+        T.kernels_launched = h->kernels_launched;
+    }
+    Y3_API_END(h)
+}
+
+int64_t y3_tile_plan(int64_t img_h, int64_t img_w, int32_t tile_h, int32_t tile_w, int32_t edge, int32_t* xs, int32_t* ys, int64_t cap) {
+    try {
+        std::vector<TileGeo> v = plan_tiles(img_h, img_w, tile_h, tile_w, edge, nullptr, nullptr);
+        for (size_t i = 0; i < v.size() && (int64_t)i < cap; ++i) {
+            if (xs) xs[i] = v[i].rec_x;
+            if (ys) ys[i] = v[i].rec_y;
+        }
+        return (int64_t)v.size();
+    } catch (const Error& e) {
+        g_create_error = e.msg;
+        return e.code;
+    }
+}
+
+namespace {
+// uploads the rows of the image that tiles [first, first+count) touch; returns the device pointer and row_lo
+const void* upload_band(y3_context* h, Tiler* T, const void* img, y3_dtype dt, y3_mem mem, int64_t W, int C,
+                        const std::vector<TileGeo>& geo, int64_t first, int64_t count, long long* row_lo) {
+    if (mem == Y3_MEM_DEVICE) { *row_lo = 0; return img; }
+    int lo = geo[first].y0, hi = geo[first].y1;
+    for (int64_t t = first; t < first + count; ++t) { lo = std::min(lo, geo[t].y0); hi = std::max(hi, geo[t].y1); }
+    const size_t row_bytes = (size_t)W * C * dtype_size(dt);
+    T->img.reserve((size_t)(hi - lo) * row_bytes);
+    Y3_CUDA(cudaMemcpyAsync(T->img.p, static_cast<const char*>(img) + (size_t)lo * row_bytes, (size_t)(hi - lo) * row_bytes,
+                            cudaMemcpyHostToDevice, h->stream));
+    *row_lo = lo;
+    return T->img.p;
+}
+const TileGeo* upload_geo(y3_context* h, Tiler* T, const std::vector<TileGeo>& geo) {
+    T->geo.reserve(geo.size() * sizeof(TileGeo));
+    Y3_CUDA(cudaMemcpyAsync(T->geo.p, geo.data(), geo.size() * sizeof(TileGeo), cudaMemcpyHostToDevice, h->stream));
+    Y3_CUDA(cudaStreamSynchronize(h->stream));     // geo is a host temporary
+    return T->geo.as<TileGeo>();
+}
+void deliver_preds(y3_context* h, Tiler* T, double* preds, y3_mem mem, int64_t cap, int64_t* n_out) {
+    *n_out = T->acc_rows;
+    Y3_CHECK(T->acc_rows <= cap, Y3_ERR_NOSPACE, "output capacity %lld < %lld boxes", (long long)cap, (long long)T->acc_rows);
+    if (T->acc_rows) {
+        Y3_CHECK(preds, Y3_ERR_INVALID, "NULL output");
+        from_device(h, preds, mem, T->acc.p, (size_t)T->acc_rows * 48);
+    }
+    Y3_CUDA(cudaStreamSynchronize(h->stream));
+}
+}  // namespace
+
+y3_status y3_tiles_normalized(y3_handle h, const void* img, y3_dtype dt, y3_mem img_mem, int64_t H, int64_t W, int32_t C,
+                              int32_t th, int32_t tw, int32_t edge, int64_t first, int64_t count, float* out, y3_mem out_mem) {
+    Y3_API_BEGIN(h)
+    Y3_CHECK(img && out && H > 0 && W > 0 && C > 0, Y3_ERR_INVALID, "bad arguments");
+    Tiler* T = tiler_of(h);
+    std::vector<TileGeo> geo = plan_tiles(H, W, th, tw, edge, nullptr, nullptr);
+    Y3_CHECK(first >= 0 && count >= 0 && first + count <= (int64_t)geo.size(), Y3_ERR_INVALID, "tile range [%lld,+%lld) outside 0..%zu",
+             (long long)first, (long long)count, geo.size());
+    if (count > 0) {
+        long long row_lo = 0;
+        const void* d_img = upload_band(h, T, img, dt, img_mem, W, C, geo, first, count, &row_lo);
+        const TileGeo* d_geo = upload_geo(h, T, geo);
+        const size_t bytes = (size_t)count * C * th * tw * 4;
+        float* dst = out_mem == Y3_MEM_DEVICE ? out : (T->tiles.reserve(bytes), T->tiles.as<float>());
+        launch_tile_norm(h, d_img, dt, row_lo, (int)W, C, d_geo + first, (int)count, th, tw, dst, nullptr);
+        if (out_mem != Y3_MEM_DEVICE) from_device(h, out, out_mem, dst, bytes);
+        Y3_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    Y3_API_END(h)
+}
+
+y3_status y3_stitch_tiles(y3_handle h, const float* dets, y3_mem dets_mem, int64_t n_per_tile, int32_t nc, int64_t H, int64_t W,
+                          int32_t th, int32_t tw, int32_t edge, int64_t first, int64_t count, float min_box, float iou_thr,
+                          float score_thr, double* preds, y3_mem preds_mem, int64_t cap, int64_t* n_out) {
+    Y3_API_BEGIN(h)
+    Y3_CHECK(n_out && n_per_tile > 0 && nc >= 1 && (count == 0 || dets), Y3_ERR_INVALID, "bad arguments");
+    Tiler* T = tiler_of(h);
+    PostProc* P = post_of(h);
+    std::vector<TileGeo> geo = plan_tiles(H, W, th, tw, edge, nullptr, nullptr);
+    Y3_CHECK(first >= 0 && count >= 0 && first + count <= (int64_t)geo.size(), Y3_ERR_INVALID, "tile range outside the plan");
+    T->acc_rows = 0;
+    *n_out = 0;
+    if (count > 0) {
+        const TileGeo* d_geo = upload_geo(h, T, geo);
+        const size_t per_tile = (size_t)n_per_tile * (5 + nc);
+        StitchArgs S{H, W, th, tw, edge};
+        // bounded batches so the candidate scratch stays small
+        const int64_t step = std::max<int64_t>(1, std::min<int64_t>(count, (int64_t)(64ll << 20) / (int64_t)per_tile));
+        for (int64_t t0 = 0; t0 < count; t0 += step) {
+            const int64_t nt = std::min(step, count - t0);
+            const float* d = static_cast<const float*>(to_device(h, dets + (size_t)t0 * per_tile, dets_mem, (size_t)nt * per_tile * 4, T->dets));
+            NmsResult R = P->run(dets_source(d, n_per_tile, (int)nt, nc, true, min_box, score_thr), iou_thr);
+            T->stitch(P, R, d_geo + first + t0, S);
+        }
+        deliver_preds(h, T, preds, preds_mem, cap, n_out);
+    }
+    Y3_API_END(h)
+}
+
+y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dt, y3_mem img_mem, int64_t H, int64_t W, int32_t C, int32_t th,
+                         int32_t tw, int32_t edge, int64_t tile_first, int64_t tile_count, float min_box, float iou_thr,
+                         float score_thr, double* preds, y3_mem preds_mem, int64_t cap, int64_t* n_out) {
+    Y3_API_BEGIN(h)
+    Net* net = net_of(h);
+    Y3_CHECK(img && n_out, Y3_ERR_INVALID, "NULL pointer");
+    Y3_CHECK(th == net->H && tw == net->W && C == net->C, Y3_ERR_INVALID,
+             "tile %dx%dx%d does not match the network input %dx%dx%d", th, tw, C, net->H, net->W, net->C);
+    Tiler* T = tiler_of(h);
+    PostProc* P = post_of(h);
+    std::vector<TileGeo> geo = plan_tiles(H, W, th, tw, edge, nullptr, nullptr);
+    if (tile_count < 0) tile_count = (int64_t)geo.size() - tile_first;
+    Y3_CHECK(tile_first >= 0 && tile_count >= 0 && tile_first + tile_count <= (int64_t)geo.size(), Y3_ERR_INVALID,
+             "tile range [%lld,+%lld) outside 0..%zu", (long long)tile_first, (long long)tile_count, geo.size());
+    y3_timings& Tm = h->timings;
+    Tm = y3_timings{};
+    Phase total(h, &Tm.ms_total);
+    T->acc_rows = 0;
+    *n_out = 0;
+    if (tile_count > 0) {
+        long long row_lo = 0;
+        const void* d_img;
+        { Phase p(h, &Tm.ms_h2d); d_img = upload_band(h, T, img, dt, img_mem, W, C, geo, tile_first, tile_count, &row_lo); p.stop(); }
+        const TileGeo* d_geo = upload_geo(h, T, geo);
+        StitchArgs S{H, W, th, tw, edge};
+        const int B = net->maxB;
+        T->tiles.reserve((size_t)B * C * th * tw * 4);
+        for (int64_t t0 = 0; t0 < tile_count; t0 += B) {
+            const int nb = (int)std::min<int64_t>(B, tile_count - t0);
+            const TileGeo* g = d_geo + tile_first + t0;
+            { Phase p(h, &Tm.ms_prep); launch_tile_norm(h, d_img, dt, row_lo, (int)W, C, g, nb, th, tw, T->tiles.as<float>(), nullptr); p.stop(); }
+            { Phase p(h, &Tm.ms_conv); net->forward(T->tiles.as<float>(), nb); p.stop(); }
+            { Phase p(h, &Tm.ms_decode); net->decode(nb); p.stop(); }
+            NmsResult R;
+            { Phase p(h, &Tm.ms_nms);
+              R = P->run(dets_source(net->boxes.as<float>(), net->rows_per_image, nb, net->nc, true, min_box, score_thr), iou_thr);
+              p.stop(); }
+            Tm.candidates += R.n_cand; Tm.kept += R.n_kept;
+            { Phase p(h, &Tm.ms_stitch); T->stitch(P, R, g, S); p.stop(); }
+        }
+        { Phase p(h, &Tm.ms_d2h); deliver_preds(h, T, preds, preds_mem, cap, n_out); p.stop(); }
+    }
+    total.stop();
+    Tm.kernels_launched = h->kernels_launched;
+    Y3_API_END(h)
+}
+
+y3_status y3_get_timings(y3_handle h, y3_timings* out) {
+    if (!h || !out) return Y3_ERR_INVALID;
+    *out = h->timings;
+    out->kernels_launched = h->kernels_launched;
+    return Y3_OK;
+}
+
+y3_status y3_bench_forward(y3_handle h, int32_t batch, int32_t iters, float* ms_per_iter) {
+    Y3_API_BEGIN(h)
+    Net* net = net_of(h);
+    Y3_CHECK(ms_per_iter && iters >= 1 && batch >= 1 && batch <= net->maxB, Y3_ERR_INVALID, "bad arguments");
+    const size_t in_bytes = (size_t)batch * net->C * net->H * net->W * 4;
+    h->stage_in.reserve(in_bytes);                 // whatever the last call left resident (or zeros)
+    net->forward(h->stage_in.as<float>(), batch);  // warm-up
+    float acc = 0.f;
+    Phase p(h, &acc);
+    for (int i = 0; i < iters; ++i) net->forward(h->stage_in.as<float>(), batch);
+    p.stop();
+    *ms_per_iter = acc / iters;
+    Y3_API_END(h)
+}
+
+y3_status y3_debug_layer_output(y3_handle h, const char* layer, int32_t batch, float* out, int64_t cap_floats, int32_t* dims) {
+    Y3_API_BEGIN(h)
+    Net* net = net_of(h);
+    Y3_CHECK(layer && out && dims, Y3_ERR_INVALID, "NULL pointer");
+    const Op* op = nullptr;
+    for (const Op& o : net->ops) if (o.name == layer) { op = &o; break; }
+    Y3_CHECK(op && op->kind != Op::DET, Y3_ERR_INVALID, "no such (non-detection) layer '%s'", layer);
+    const TensorInfo& t = net->tensors[op->out.t];
+    dims[0] = op->out.c; dims[1] = t.h; dims[2] = t.w;
+    const int64_t n = (int64_t)batch * op->out.c * t.h * t.w;
+    Y3_CHECK(n <= cap_floats, Y3_ERR_NOSPACE, "need %lld floats", (long long)n);
+    h->stage_out.reserve((size_t)n * 4);
+    slice_to_nchw(h, reinterpret_cast<const __nv_bfloat16*>(t.ptr), h->stage_out.as<float>(), batch, t.h, t.w, op->out.c, t.c, op->out.coff);
+    from_device(h, out, Y3_MEM_HOST, h->stage_out.p, (size_t)n * 4);
+    Y3_CUDA(cudaStreamSynchronize(h->stream));
+    Y3_API_END(h)
+}
+
+}  // extern "C"

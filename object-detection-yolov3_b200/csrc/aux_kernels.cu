@@ -1,0 +1,221 @@
+// aux_kernels.cu - the non-GEMM kernels around the conv stack:
+//   k_stem            first conv_layer (model.py:385): 3x3 s1, Cimg (1 or 3) -> 32, read straight from
+//                     the NCHW fp32 batch, fused bias -> leaky(0.2) -> BN, NHWC bf16 out.  K = 9*Cimg is
+//                     9..27: far too thin for a 128-wide UMMA tile and the layer is output-bandwidth
+//                     bound (64 B written per pixel for <= 27 reads), so it runs on the FP32 pipe.
+//   k_pack_conv_w     Keras Conv2D kernel [kh,kw,Cin,Cout] fp32 -> [Cout_pad][kh*kw*Cin] bf16 (K-major)
+//   k_pack_convt_w    Keras Conv2DTranspose kernel [2,2,Cout,Cin] fp32 -> 4 x [Cout][Cin] bf16
+//   k_bn_fold         (gamma,beta,mean,var) -> s = gamma/sqrt(var+1e-3), t = beta - mean*s  (SURVEY Q1,Q3)
+//   k_heads_to_nchw   [B,HW,pitch] fp32 -> NCHW fp32 (the parity point of y3_forward_heads)
+//   k_decode          reorg_layer + convert_feature_map_to_inference_detections (model.py:122-212)
+#include "aux_kernels.cuh"
+
+namespace y3 {
+
+// ------------------------------------------------------------------------------------------ stem
+template <int CIN>
+__global__ void __launch_bounds__(128)
+k_stem(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, const float* __restrict__ w /*[9*CIN][32]*/,
+       const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
+       int B, int H, int W) {
+    __shared__ float4 s_w[9 * CIN * 8];
+    __shared__ float4 s_p[3 * 8];
+    for (int i = threadIdx.x; i < 9 * CIN * 8; i += blockDim.x) s_w[i] = reinterpret_cast<const float4*>(w)[i];
+    if (threadIdx.x < 8) {
+        s_p[threadIdx.x] = reinterpret_cast<const float4*>(bias)[threadIdx.x];
+        s_p[8 + threadIdx.x] = reinterpret_cast<const float4*>(scale)[threadIdx.x];
+        s_p[16 + threadIdx.x] = reinterpret_cast<const float4*>(shift)[threadIdx.x];
+    }
+    __syncthreads();
+    const long long npix = (long long)B * H * W;
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
+         pix += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(pix % W);
+        const long long t = pix / W;
+        const int y = (int)(t % H);
+        const int b = (int)(t / H);
+        float acc[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int yy = y + kh - 1;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int xx = x + kw - 1;
+                const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) {
+                    const float v = ok ? __ldg(in + (((long long)b * CIN + ci) * H + yy) * W + xx) : 0.f;
+                    const float4* wr = s_w + ((kh * 3 + kw) * CIN + ci) * 8;
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const float4 ww = wr[c4];
+                        acc[4 * c4 + 0] = fmaf(v, ww.x, acc[4 * c4 + 0]);
+                        acc[4 * c4 + 1] = fmaf(v, ww.y, acc[4 * c4 + 1]);
+                        acc[4 * c4 + 2] = fmaf(v, ww.z, acc[4 * c4 + 2]);
+                        acc[4 * c4 + 3] = fmaf(v, ww.w, acc[4 * c4 + 3]);
+                    }
+                }
+            }
+        }
+        uint32_t o[16];
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 bb = s_p[c4], ss = s_p[8 + c4], tt = s_p[16 + c4];
+            float z0 = acc[4 * c4 + 0] + bb.x, z1 = acc[4 * c4 + 1] + bb.y;
+            float z2 = acc[4 * c4 + 2] + bb.z, z3 = acc[4 * c4 + 3] + bb.w;
+            z0 = (z0 > 0.f ? z0 : 0.2f * z0) * ss.x + tt.x;
+            z1 = (z1 > 0.f ? z1 : 0.2f * z1) * ss.y + tt.y;
+            z2 = (z2 > 0.f ? z2 : 0.2f * z2) * ss.z + tt.z;
+            z3 = (z3 > 0.f ? z3 : 0.2f * z3) * ss.w + tt.w;
+            __nv_bfloat162 a = __floats2bfloat162_rn(z0, z1), c = __floats2bfloat162_rn(z2, z3);
+            o[2 * c4] = *reinterpret_cast<uint32_t*>(&a);
+            o[2 * c4 + 1] = *reinterpret_cast<uint32_t*>(&c);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + pix * 32);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+        dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
+    }
+}
+
+void launch_stem(y3_context* ctx, const float* in, __nv_bfloat16* out, const float* w, const float* bias,
+                 const float* scale, const float* shift, int B, int H, int W, int cin) {
+    const long long npix = (long long)B * H * W;
+    const int blocks = (int)std::min<long long>((npix + 127) / 128, (long long)ctx->sm_count * 64);
+    if (cin == 1) k_stem<1><<<blocks, 128, 0, ctx->stream>>>(in, out, w, bias, scale, shift, B, H, W);
+    else if (cin == 3) k_stem<3><<<blocks, 128, 0, ctx->stream>>>(in, out, w, bias, scale, shift, B, H, W);
+    else if (cin == 2) k_stem<2><<<blocks, 128, 0, ctx->stream>>>(in, out, w, bias, scale, shift, B, H, W);
+    else if (cin == 4) k_stem<4><<<blocks, 128, 0, ctx->stream>>>(in, out, w, bias, scale, shift, B, H, W);
+    else fail(Y3_ERR_UNSUPPORTED, "stem supports 1..4 image channels, got %d", cin);
+    Y3_LAUNCHED(ctx);
+}
+
+// ------------------------------------------------------------------------------------------ packing
+__global__ void k_pack_conv_w(const float* __restrict__ k /*[taps,Cin,Cout]*/, __nv_bfloat16* __restrict__ out,
+                              int taps, int cin, int cout, int cout_pad) {
+    const long long n = (long long)cout_pad * taps * cin;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % cin);
+        const long long r = i / cin;
+        const int tap = (int)(r % taps);
+        const int co = (int)(r / taps);
+        const float v = co < cout ? k[((long long)tap * cin + ci) * cout + co] : 0.f;
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+__global__ void k_pack_convt_w(const float* __restrict__ k /*[4,Cout,Cin]*/, __nv_bfloat16* __restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = __float2bfloat16_rn(k[i]);
+}
+__global__ void k_bn_fold(const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ m,
+                          const float* __restrict__ v, float* __restrict__ s, float* __restrict__ t, int c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    const float sc = g[i] / sqrtf(v[i] + 1e-3f);
+    s[i] = sc;
+    t[i] = b[i] - m[i] * sc;
+}
+
+void pack_conv_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, int taps, int cin, int cout, int cout_pad) {
+    const long long n = (long long)cout_pad * taps * cin;
+    k_pack_conv_w<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, ctx->stream>>>(k, out, taps, cin, cout, cout_pad);
+    Y3_LAUNCHED(ctx);
+}
+void pack_convt_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, long long n) {
+    k_pack_convt_w<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, ctx->stream>>>(k, out, n);
+    Y3_LAUNCHED(ctx);
+}
+void bn_fold(y3_context* ctx, const float* g, const float* b, const float* m, const float* v, float* s, float* t, int c) {
+    k_bn_fold<<<(c + 127) / 128, 128, 0, ctx->stream>>>(g, b, m, v, s, t, c);
+    Y3_LAUNCHED(ctx);
+}
+
+// ------------------------------------------------------------------------------------------ heads
+__global__ void k_heads_to_nchw(const float* __restrict__ in, float* __restrict__ out, int B, int HW, int C, int pitch) {
+    const long long n = (long long)B * C * HW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i % HW);
+        const long long r = i / HW;
+        const int c = (int)(r % C);
+        const int b = (int)(r / C);
+        out[i] = in[((long long)b * HW + p) * pitch + c];
+    }
+}
+void heads_to_nchw(y3_context* ctx, const float* in, float* out, int B, int HW, int C, int pitch) {
+    const long long n = (long long)B * C * HW;
+    k_heads_to_nchw<<<(int)std::min<long long>((n + 255) / 256, 8192), 256, 0, ctx->stream>>>(in, out, B, HW, C, pitch);
+    Y3_LAUNCHED(ctx);
+}
+
+__global__ void k_slice_to_nchw(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
+                                int pitch, int coff) {
+    const long long n = (long long)B * C * H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        long long r = i / W;
+        const int y = (int)(r % H); r /= H;
+        const int c = (int)(r % C);
+        const int b = (int)(r / C);
+        out[i] = __bfloat162float(in[(((long long)b * H + y) * W + x) * pitch + coff + c]);
+    }
+}
+void slice_to_nchw(y3_context* ctx, const __nv_bfloat16* in, float* out, int B, int H, int W, int C, int pitch, int coff) {
+    const long long n = (long long)B * C * H * W;
+    k_slice_to_nchw<<<(int)std::min<long long>((n + 255) / 256, 8192), 256, 0, ctx->stream>>>(in, out, B, H, W, C, pitch, coff);
+    Y3_LAUNCHED(ctx);
+}
+
+// ------------------------------------------------------------------------------------------ decode
+// One thread per output element of [B, N, 5+NC].  A head stored NHWC with channel a*(5+NC)+k is already
+// in output row order, so this is a pure element-wise map.  Arithmetic is fp32 in the
+// reference's operand order with no FMA contraction:
+//   cx = (sigmoid(tx) + j) * stride ; w = exp(tw) * anchor_w ; x0 = cx - w / 2 ; x1 = cx + w / 2
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+__global__ void __launch_bounds__(256)
+k_decode(DecodeArgs D, float* __restrict__ out) {
+    const int E = 5 + D.nc;
+    const long long per_img = (long long)D.n_total * E;
+    const long long n = per_img * D.batch;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per_img);
+        const long long r = i - (long long)b * per_img;
+        const int row = (int)(r / E);
+        const int k = (int)(r - (long long)row * E);
+        int s = 0;
+        if (row >= D.row_start[1]) s = 1;
+        if (row >= D.row_start[2]) s = 2;
+        const int lr = row - D.row_start[s];
+        const int cell = lr / D.na;
+        const int a = lr - cell * D.na;
+        const float* hp = D.head[s] + ((long long)b * D.gh[s] * D.gw[s] + cell) * D.pitch + a * E;
+        float v;
+        if (k >= 4) {
+            v = sigmoid_f(__ldg(hp + k));
+        } else {
+            const int axis = k & 1;                         // 0: x, 1: y
+            const float tc = __ldg(hp + axis);
+            const float ts = __ldg(hp + 2 + axis);
+            const int gi = cell / D.gw[s], gj = cell - gi * D.gw[s];
+            const float off = axis == 0 ? (float)gj : (float)gi;
+            // model.py:127,157 - the (h,w) stride pair multiplies the (x,y) pair as written
+            const float stride = axis == 0 ? D.stride_h[s] : D.stride_w[s];
+            const float c = __fmul_rn(__fadd_rn(sigmoid_f(tc), off), stride);
+            const float wh = __fmul_rn(expf(ts), axis == 0 ? D.anchor_w[a] : D.anchor_h[a]);
+            const float half = __fdiv_rn(wh, 2.0f);
+            v = (k < 2) ? __fsub_rn(c, half) : __fadd_rn(c, half);
+        }
+        out[i] = v;
+    }
+}
+void launch_decode(y3_context* ctx, const DecodeArgs& D, float* out) {
+    const long long n = (long long)D.n_total * (5 + D.nc) * D.batch;
+    const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
+    k_decode<<<blocks, 256, 0, ctx->stream>>>(D, out);
+    Y3_LAUNCHED(ctx);
+}
+
+}  // namespace y3

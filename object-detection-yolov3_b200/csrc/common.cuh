@@ -1,0 +1,128 @@
+// common.cuh - context, error handling and small device helpers shared by all translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <memory>
+
+#include "../../include/yolo3_b200.h"
+
+namespace y3 {
+
+struct Error {
+    y3_status code;
+    std::string msg;
+};
+
+// Thrown inside the library, caught at the extern "C" boundary (api.cu) - never crosses the ABI.
+[[noreturn]] void fail(y3_status code, const char* fmt, ...);
+
+#define Y3_CUDA(expr)                                                                       \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            ::y3::fail(Y3_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                       __FILE__, __LINE__);                                                 \
+    } while (0)
+
+#define Y3_CHECK(cond, code, ...)                      \
+    do {                                               \
+        if (!(cond)) ::y3::fail((code), __VA_ARGS__);  \
+    } while (0)
+
+// Growable device buffer (never shrinks; freed with the context).
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes);
+    void release();
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes);
+    void release();
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+    ~PinnedBuf() { release(); }
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf&) = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
+};
+
+struct EventTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    void init();
+    void destroy();
+    void start(cudaStream_t s) { cudaEventRecord(a, s); }
+    void stop(cudaStream_t s) { cudaEventRecord(b, s); }
+    float ms();  // synchronises on b
+};
+
+struct Net;        // net.cu
+struct PostProc;   // nms.cu
+struct Tiler;      // tiles.cu
+
+}  // namespace y3
+
+struct y3_context {
+    y3_config cfg{};
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    int64_t kernels_launched = 0;
+    y3_timings timings{};
+    y3::Net* net = nullptr;
+    y3::PostProc* post = nullptr;
+    y3::Tiler* tiler = nullptr;
+    y3::DevBuf stage_in, stage_out, stage_aux;   // host<->device staging for API calls
+    y3::PinnedBuf pin_small;
+};
+
+namespace y3 {
+
+inline void count_launch(y3_context* c, int n = 1) { c->kernels_launched += n; }
+
+// Checks the launch and counts it.
+#define Y3_LAUNCHED(ctx)                \
+    do {                                \
+        Y3_CUDA(cudaGetLastError());    \
+        ::y3::count_launch((ctx));      \
+    } while (0)
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+static inline int ilog2_ceil(uint64_t v) { int b = 0; while ((1ull << b) < v) ++b; return b; }
+
+// ---- fp32 helpers that reproduce NumPy semantics exactly (no contraction, NaN propagation) ----
+__device__ __forceinline__ float np_max(float a, float b) { return (a >= b || a != a) ? a : b; }
+__device__ __forceinline__ float np_min(float a, float b) { return (a <= b || a != a) ? a : b; }
+
+// bbox_utils.compute_iou (bbox_utils.py:200-214) for one pair, bit-exact with NumPy fp32:
+//   inter = max(yb - yt, 0) * max(xr - xl, 0); union = (area_a + area_b) - inter; iou = inter / union
+__device__ __forceinline__ float iou_exact(const float4 a, const float area_a, const float4 b, const float area_b) {
+    const float xl = np_max(a.x, b.x);
+    const float yt = np_max(a.y, b.y);
+    const float xr = np_min(a.z, b.z);
+    const float yb = np_min(a.w, b.w);
+    const float dh = np_max(__fsub_rn(yb, yt), 0.0f);
+    const float dw = np_max(__fsub_rn(xr, xl), 0.0f);
+    const float inter = __fmul_rn(dh, dw);
+    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    return __fdiv_rn(inter, uni);
+}
+__device__ __forceinline__ float box_area_exact(const float4 b) {
+    return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+
+}  // namespace y3

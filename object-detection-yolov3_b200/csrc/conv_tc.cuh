@@ -1,0 +1,40 @@
+// conv_tc.cuh - host-side description of one tcgen05 implicit-GEMM convolution launch.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace y3 {
+
+// Everything the kernel needs besides the four tensor maps.
+struct ConvArgs {
+    int tiles_x, tiles_y, tiles_per_img, n_img;
+    int n_tiles_n, total_tiles;
+    int BH, BW;              // spatial patch of one M tile (BH*BW <= 128 rows)
+    int taps, kwn;           // 9/3 for 3x3, 1/1 for 1x1
+    int cin, kchunks;        // channels per tap, cin / BK
+    int stride, pad;         // 1|2 ; left/top zero padding (TF SAME: s1 k3 -> 1, s2 -> 0)
+    int a_cpitch;            // channel pitch of the input buffer (phase offset of the stride-2 view)
+    int has_res, linear, out_f32;
+    int Ho, Wo;
+    const float* bias;       // [cout_pad]
+    const float* scale;      // [cout_pad]  gamma / sqrt(var + eps)       (unused when linear)
+    const float* shift;      // [cout_pad]  beta - mean * scale
+    float* out32;            // fp32 NHWC output (detection heads), pitch floats per pixel
+    long long out32_pitch;
+    int cout_valid;
+};
+
+struct ConvLaunch {
+    CUtensorMap map_a, map_b, map_out, map_res;
+    ConvArgs args;
+    int bn, bk;              // template selection
+    int grid;
+};
+
+// Encodes a tiled tensor map (bf16) through the driver entry point fetched at runtime.
+void encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box, int swizzle_bytes);
+
+void launch_conv(y3_context* ctx, const ConvLaunch& L);
+
+}  // namespace y3

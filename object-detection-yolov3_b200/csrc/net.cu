@@ -1,0 +1,462 @@
+// net.cu - the YOLOv3 graph of the reference (model.py:356-421: darknet53_feature_extractor +
+// build_feature_maps) as a static plan of tcgen05 conv launches over NHWC bf16 buffers.
+//
+//   * layer list in the reference's creation order, so Keras auto-names (conv2d_k,
+//     batch_normalization_k, conv2d_transpose[_1], feature_map_1..3) map 1:1 onto ops;
+//   * feature_block residual adds the BLOCK INPUT on every repetition (model.py:43-47);
+//   * bridge convs keep the route's width and the concat is [upsampled, route] (Q7) - realised
+//     zero-copy: the last conv of mb3 / mb4 and the transposed conv write channel slices of one
+//     wider buffer, the consumers read it through tensor maps;
+//   * upsample_2x is a general Conv2DTranspose(k=2,s=2) = four 1x1 GEMMs scattered by the output
+//     tensor map (works for any kernel, incl. the reference's all-ones one, Q6);
+//   * activation buffers are assigned by liveness (linear scan) so consecutive layers reuse the
+//     same few buffers and stay L2-resident at small batch.
+#include "net.cuh"
+
+#include <algorithm>
+#include <stdlib.h>
+
+namespace y3 {
+
+
+// ------------------------------------------------------------------------------------------ plan
+int Net::new_tensor(int h, int w, int c) {
+    TensorInfo t;
+    t.h = h; t.w = w; t.c = c;
+    tensors.push_back(t);
+    return (int)tensors.size() - 1;
+}
+
+static std::string suffix(int k) { return k == 0 ? std::string() : "_" + std::to_string(k); }
+
+View Net::add_conv(View in, int cout, int k, int stride, int res_t, View forced_out) {
+    Op op;
+    op.kind = Op::CONV;
+    op.name = "conv2d" + suffix(n_conv++);
+    op.bn = "batch_normalization" + suffix(n_bn++);
+    op.cin = in.c; op.cout = cout; op.cout_pad = cout; op.k = k; op.stride = stride;
+    op.in = in; op.res_t = res_t;
+    const TensorInfo& ti = tensors[in.t];
+    const int ho = ti.h / stride, wo = ti.w / stride;
+    if (forced_out.t >= 0) op.out = forced_out;
+    else { op.out.t = new_tensor(ho, wo, cout); op.out.coff = 0; op.out.c = cout; }
+    ops.push_back(std::move(op));
+    return ops.back().out;
+}
+
+View Net::add_block(View x, int reps, View final_out) {
+    const int c = x.c;
+    View y = x;
+    for (int r = 0; r < reps; ++r) {
+        View a = add_conv(y, c / 2, 1, 1);
+        View fo;                      // default: fresh tensor
+        if (r == reps - 1) fo = final_out;
+        y = add_conv(a, c, 3, 1, x.t, fo);
+        ops.back().res = x;
+    }
+    return y;
+}
+
+void Net::add_yolo(View in, int f, View* route, View* out) {
+    View x = add_conv(in, f / 2, 1, 1);
+    x = add_conv(x, f, 3, 1);
+    x = add_conv(x, f / 2, 1, 1);
+    x = add_conv(x, f, 3, 1);
+    x = add_conv(x, f / 2, 1, 1);
+    *route = x;
+    *out = add_conv(x, f, 3, 1);
+}
+
+void Net::add_det(View in, int idx) {
+    Op op;
+    op.kind = Op::DET;
+    op.name = "feature_map_" + std::to_string(idx + 1);
+    op.cin = in.c; op.cout = det_c; op.cout_pad = HEAD_PITCH; op.k = 1; op.stride = 1;
+    op.in = in; op.head = idx;
+    Y3_CHECK(det_c <= HEAD_PITCH, Y3_ERR_UNSUPPORTED, "A*(5+NC) = %d exceeds %d head channels", det_c, HEAD_PITCH);
+    ops.push_back(std::move(op));
+}
+
+void Net::add_convt(View in, View out) {
+    Op op;
+    op.kind = Op::CONVT;
+    op.name = "conv2d_transpose" + suffix(n_convt++);
+    op.cin = in.c; op.cout = out.c; op.cout_pad = out.c; op.k = 2; op.stride = 2;
+    op.in = in; op.out = out;
+    ops.push_back(std::move(op));
+}
+
+void Net::build() {
+    const y3_config& c = ctx->cfg;
+    H = c.img_h; W = c.img_w; C = c.img_c; nc = c.num_classes; na = c.num_anchors; maxB = c.max_batch;
+    Y3_CHECK(H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, Y3_ERR_INVALID, "image size %dx%d must be a multiple of 32", H, W);
+    Y3_CHECK(C >= 1 && C <= 4, Y3_ERR_UNSUPPORTED, "image channels %d not in 1..4", C);
+    Y3_CHECK(na >= 1 && na <= Y3_MAX_ANCHORS && nc >= 1 && maxB >= 1, Y3_ERR_INVALID, "bad anchors/classes/batch");
+    det_c = na * (5 + nc);
+    for (int s = 0; s < 3; ++s) { gh[s] = H / (32 >> s); gw[s] = W / (32 >> s); }
+    rows_per_image = 0;
+    for (int s = 0; s < 3; ++s) { row_start[s] = (int)rows_per_image; rows_per_image += (int64_t)gh[s] * gw[s] * na; }
+
+    // --- layer list (creation order of model.py:383-421, 356-380)
+    Op stem;
+    stem.kind = Op::STEM;
+    stem.name = "conv2d" + suffix(n_conv++);
+    stem.bn = "batch_normalization" + suffix(n_bn++);
+    stem.cin = C; stem.cout = 32; stem.cout_pad = 32; stem.k = 3; stem.stride = 1;
+    stem.out.t = new_tensor(H, W, 32); stem.out.coff = 0; stem.out.c = 32;
+    ops.push_back(std::move(stem));
+    View x = ops.back().out;
+
+    const int cat3 = new_tensor(H / 8, W / 8, 512);      // [up(256) | route1(256)]
+    const int cat2 = new_tensor(H / 16, W / 16, 1024);   // [up(512) | route2(512)]
+    View none;
+
+    x = add_conv(x, 64, 3, 2);
+    x = add_block(x, 1, none);
+    x = add_conv(x, 128, 3, 2);
+    x = add_block(x, 2, none);
+    x = add_conv(x, 256, 3, 2);
+    View r1; r1.t = cat3; r1.coff = 256; r1.c = 256;
+    x = add_block(x, 8, r1);
+    x = add_conv(x, 512, 3, 2);
+    View r2; r2.t = cat2; r2.coff = 512; r2.c = 512;
+    x = add_block(x, 8, r2);
+    x = add_conv(x, 1024, 3, 2);
+    x = add_block(x, 4, none);
+
+    View route, out;
+    add_yolo(x, 1024, &route, &out);
+    add_det(out, 0);
+    x = add_conv(route, 512, 1, 1);
+    { View up; up.t = cat2; up.coff = 0; up.c = 512; add_convt(x, up); }
+    { View in; in.t = cat2; in.coff = 0; in.c = 1024; add_yolo(in, 512, &route, &out); }
+    add_det(out, 1);
+    x = add_conv(route, 256, 1, 1);
+    { View up; up.t = cat3; up.coff = 0; up.c = 256; add_convt(x, up); }
+    { View in; in.t = cat3; in.coff = 0; in.c = 512; add_yolo(in, 256, &route, &out); }
+    add_det(out, 2);
+
+    // --- liveness + buffer assignment (linear scan, exact-size free lists)
+    for (size_t i = 0; i < ops.size(); ++i) {
+        Op& op = ops[i];
+        auto use = [&](int t) { if (t >= 0) { if (tensors[t].first < 0) tensors[t].first = (int)i; tensors[t].last = (int)i; } };
+        if (op.kind != Op::STEM) use(op.in.t);
+        if (op.res_t >= 0) use(op.res_t);
+        if (op.kind != Op::DET) use(op.out.t);
+    }
+    std::multimap<size_t, void*> free_list;
+    const bool no_reuse = getenv("Y3_DEBUG_NO_REUSE") != nullptr;   // keep every layer output (tests)
+    for (size_t i = 0; i < ops.size(); ++i) {
+        for (size_t t = 0; t < tensors.size(); ++t) {
+            TensorInfo& ti = tensors[t];
+            if (ti.first != (int)i) continue;
+            const size_t bytes = (size_t)maxB * ti.h * ti.w * ti.c * 2;
+            auto it = free_list.lower_bound(bytes);
+            if (!no_reuse && it != free_list.end() && it->first <= bytes * 2) {
+                ti.ptr = it->second; ti.bytes = it->first;
+                free_list.erase(it);
+            } else {
+                void* p = nullptr;
+                Y3_CUDA(cudaMalloc(&p, bytes));
+                owned.push_back(p);
+                ti.ptr = p; ti.bytes = bytes;
+                act_bytes += bytes;
+            }
+        }
+        for (size_t t = 0; t < tensors.size(); ++t)
+            if (tensors[t].last == (int)i && tensors[t].ptr) free_list.insert({tensors[t].bytes, tensors[t].ptr});
+    }
+    for (int s = 0; s < 3; ++s) {
+        const size_t bytes = (size_t)maxB * gh[s] * gw[s] * HEAD_PITCH * 4;
+        Y3_CUDA(cudaMalloc((void**)&head[s], bytes));
+        owned.push_back(head[s]);
+    }
+
+    // --- parameters + launch descriptors
+    conv_flops_per_image = 0;
+    for (Op& op : ops) {
+        const int taps = op.k * op.k;
+        if (op.kind == Op::STEM) {
+            op.w.reserve((size_t)taps * op.cin * 32 * 4);
+        } else if (op.kind == Op::CONVT) {
+            op.w.reserve((size_t)4 * op.cout * op.cin * 2);
+        } else {
+            op.w.reserve((size_t)op.cout_pad * taps * op.cin * 2);
+        }
+        op.bias.reserve((size_t)op.cout_pad * 4);
+        op.scale.reserve((size_t)op.cout_pad * 4);
+        op.shift.reserve((size_t)op.cout_pad * 4);
+        op.bn_raw.reserve((size_t)4 * op.cout_pad * 4);
+        Y3_CUDA(cudaMemset(op.bias.p, 0, (size_t)op.cout_pad * 4));
+        Y3_CUDA(cudaMemset(op.scale.p, 0, (size_t)op.cout_pad * 4));
+        Y3_CUDA(cudaMemset(op.shift.p, 0, (size_t)op.cout_pad * 4));
+        if (op.kind != Op::CONVT) {
+            const TensorInfo* to = op.kind == Op::DET ? nullptr : &tensors[op.out.t];
+            const int ho = to ? to->h : gh[op.head], wo = to ? to->w : gw[op.head];
+            conv_flops_per_image += 2.0 * ho * wo * op.cout * taps * op.cin;
+        }
+        if (op.kind != Op::STEM) make_launches(op);
+    }
+    boxes.reserve((size_t)maxB * rows_per_image * (5 + nc) * 4);
+}
+
+static void pick_patch(int ho, int wo, int* bh, int* bw) {
+    double best = -1;
+    int bbh = 1, bbw = 1;
+    for (int w = 1; w <= std::min(wo, 128); ++w) {
+        const int h = std::min(ho, 128 / w);
+        if (h < 1) continue;
+        const long long tiles = (long long)((wo + w - 1) / w) * ((ho + h - 1) / h);
+        const double eff = (double)ho * wo / (double)(tiles * 128);
+        if (eff > best + 1e-9 || (eff > best - 1e-9 && w > bbw)) { best = eff; bbh = h; bbw = w; }
+    }
+    *bh = bbh; *bw = bbw;
+}
+
+void Net::make_launches(Op& op) {
+    const TensorInfo& ti = tensors[op.in.t];
+    const __nv_bfloat16* in_base = reinterpret_cast<const __nv_bfloat16*>(ti.ptr) + op.in.coff;
+    const int cin = op.cin, pitch_in = ti.c;
+    const int bk = cin % 64 == 0 ? 64 : 32;
+    Y3_CHECK(cin % bk == 0, Y3_ERR_UNSUPPORTED, "layer %s: Cin %d not a multiple of 32", op.name.c_str(), cin);
+    int bn = op.cout_pad >= 128 ? 128 : op.cout_pad;
+    if (bk == 32) Y3_CHECK(bn == 64, Y3_ERR_UNSUPPORTED, "layer %s: Cin 32 needs Cout 64", op.name.c_str());
+    Y3_CHECK(bn == 128 || bn == 64 || bn == 32, Y3_ERR_UNSUPPORTED, "layer %s: Cout %d unsupported", op.name.c_str(), op.cout_pad);
+    const int oc = bn < 64 ? bn : 64;
+    const int n_sub = op.kind == Op::CONVT ? 4 : 1;
+    const int taps = op.kind == Op::CONVT ? 1 : op.k * op.k;
+    const bool flat = (op.k == 1 && op.kind != Op::CONVT);
+
+    for (int sub = 0; sub < n_sub; ++sub) {
+        ConvLaunch L;
+        memset(&L, 0, sizeof(L));
+        ConvArgs& A = L.args;
+        L.bn = bn; L.bk = bk;
+        A.taps = taps; A.kwn = op.k == 3 ? 3 : 1;
+        A.cin = cin; A.kchunks = cin / bk;
+        A.stride = op.kind == Op::CONVT ? 1 : op.stride;
+        A.pad = (op.k == 3 && op.stride == 1) ? 1 : 0;
+        A.a_cpitch = pitch_in;
+        A.has_res = op.res_t >= 0; A.linear = op.kind != Op::CONV; A.out_f32 = op.kind == Op::DET;
+        A.bias = op.bias.as<float>(); A.scale = op.scale.as<float>(); A.shift = op.shift.as<float>();
+        A.cout_valid = op.cout;
+        A.n_tiles_n = op.cout_pad / bn;
+        op.flat = flat;
+
+        // ---- A operand
+        if (flat) {
+            const uint64_t M = (uint64_t)maxB * ti.h * ti.w;
+            A.BH = 1; A.BW = 128; A.Ho = 1; op.pix_per_img = ti.h * ti.w;
+            uint64_t dims[4] = {(uint64_t)cin, M, 1, 1};
+            uint64_t str[3] = {(uint64_t)pitch_in * 2, M * pitch_in * 2, M * pitch_in * 2};
+            uint32_t box[4] = {(uint32_t)bk, 128, 1, 1};
+            encode_tmap_bf16(&L.map_a, in_base, 4, dims, str, box, bk * 2);
+        } else if (A.stride == 1) {
+            const int ho = ti.h, wo = ti.w;
+            pick_patch(ho, wo, &A.BH, &A.BW);
+            A.Ho = ho; A.Wo = wo;
+            uint64_t dims[4] = {(uint64_t)cin, (uint64_t)ti.w, (uint64_t)ti.h, (uint64_t)maxB};
+            uint64_t str[3] = {(uint64_t)pitch_in * 2, (uint64_t)ti.w * pitch_in * 2, (uint64_t)ti.h * ti.w * pitch_in * 2};
+            uint32_t box[4] = {(uint32_t)bk, (uint32_t)A.BW, (uint32_t)A.BH, 1};
+            encode_tmap_bf16(&L.map_a, in_base, 4, dims, str, box, bk * 2);
+        } else {
+            const int ho = ti.h / 2, wo = ti.w / 2;
+            pick_patch(ho, wo, &A.BH, &A.BW);
+            A.Ho = ho; A.Wo = wo;
+            // 5-D phase view: c' = pw*pitch + c, wo, ph, ho, n   (input x = 2*wo + pw, y = 2*ho + ph)
+            uint64_t dims[5] = {(uint64_t)(pitch_in + cin), (uint64_t)wo, 2, (uint64_t)ho, (uint64_t)maxB};
+            uint64_t str[4] = {(uint64_t)2 * pitch_in * 2, (uint64_t)ti.w * pitch_in * 2, (uint64_t)2 * ti.w * pitch_in * 2,
+                               (uint64_t)ti.h * ti.w * pitch_in * 2};
+            uint32_t box[5] = {(uint32_t)bk, (uint32_t)A.BW, 1, (uint32_t)A.BH, 1};
+            encode_tmap_bf16(&L.map_a, in_base, 5, dims, str, box, bk * 2);
+        }
+        // ---- B operand (weights, K-major)
+        {
+            const uint64_t ktot = (uint64_t)taps * cin;
+            const __nv_bfloat16* wbase = op.w.as<__nv_bfloat16>() + (size_t)sub * op.cout * cin;
+            uint64_t dims[2] = {ktot, (uint64_t)op.cout_pad};
+            uint64_t str[1] = {ktot * 2};
+            uint32_t box[2] = {(uint32_t)bk, (uint32_t)bn};
+            encode_tmap_bf16(&L.map_b, wbase, 2, dims, str, box, bk * 2);
+        }
+        // ---- output
+        if (op.kind == Op::DET) {
+            A.out32 = head[op.head];
+            A.out32_pitch = HEAD_PITCH;
+            L.map_out = L.map_a;   // unused
+            L.map_res = L.map_a;
+        } else {
+            const TensorInfo& to = tensors[op.out.t];
+            __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(to.ptr) + op.out.coff;
+            const int po = to.c;
+            if (flat) {
+                const uint64_t M = (uint64_t)maxB * to.h * to.w;
+                uint64_t dims[4] = {(uint64_t)op.cout, M, 1, 1};
+                uint64_t str[3] = {(uint64_t)po * 2, M * po * 2, M * po * 2};
+                uint32_t box[4] = {(uint32_t)oc, 128, 1, 1};
+                encode_tmap_bf16(&L.map_out, obase, 4, dims, str, box, oc * 2);
+            } else if (op.kind == Op::CONVT) {
+                const int i = sub >> 1, j = sub & 1;
+                // out[n, 2h+i, 2w+j, co] : same tile coordinates as the input, doubled strides
+                obase += ((size_t)i * to.w + j) * po;
+                A.Ho = ti.h; A.Wo = ti.w;
+                uint64_t dims[4] = {(uint64_t)op.cout, (uint64_t)ti.w, (uint64_t)ti.h, (uint64_t)maxB};
+                uint64_t str[3] = {(uint64_t)2 * po * 2, (uint64_t)2 * to.w * po * 2, (uint64_t)to.h * to.w * po * 2};
+                uint32_t box[4] = {(uint32_t)oc, (uint32_t)A.BW, (uint32_t)A.BH, 1};
+                encode_tmap_bf16(&L.map_out, obase, 4, dims, str, box, oc * 2);
+            } else {
+                uint64_t dims[4] = {(uint64_t)op.cout, (uint64_t)to.w, (uint64_t)to.h, (uint64_t)maxB};
+                uint64_t str[3] = {(uint64_t)po * 2, (uint64_t)to.w * po * 2, (uint64_t)to.h * to.w * po * 2};
+                uint32_t box[4] = {(uint32_t)oc, (uint32_t)A.BW, (uint32_t)A.BH, 1};
+                encode_tmap_bf16(&L.map_out, obase, 4, dims, str, box, oc * 2);
+            }
+            if (A.has_res) {
+                const TensorInfo& tr = tensors[op.res.t];
+                const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(tr.ptr) + op.res.coff;
+                uint64_t dims[4] = {(uint64_t)op.res.c, (uint64_t)tr.w, (uint64_t)tr.h, (uint64_t)maxB};
+                uint64_t str[3] = {(uint64_t)tr.c * 2, (uint64_t)tr.w * tr.c * 2, (uint64_t)tr.h * tr.w * tr.c * 2};
+                uint32_t box[4] = {(uint32_t)oc, (uint32_t)A.BW, (uint32_t)A.BH, 1};
+                encode_tmap_bf16(&L.map_res, rbase, 4, dims, str, box, oc * 2);
+            } else {
+                L.map_res = L.map_out;
+            }
+        }
+        op.launches.push_back(L);
+    }
+}
+
+void Net::set_batch(Op& op, int b) {
+    for (ConvLaunch& L : op.launches) {
+        ConvArgs& A = L.args;
+        if (op.flat) {
+            const long long M = (long long)b * op.pix_per_img;
+            A.Wo = (int)M;
+            A.tiles_x = (int)((M + 127) / 128); A.tiles_y = 1;
+            A.tiles_per_img = A.tiles_x; A.n_img = 1;
+        } else {
+            A.tiles_x = (A.Wo + A.BW - 1) / A.BW; A.tiles_y = (A.Ho + A.BH - 1) / A.BH;
+            A.tiles_per_img = A.tiles_x * A.tiles_y; A.n_img = b;
+        }
+        A.total_tiles = A.tiles_per_img * A.n_img * A.n_tiles_n;
+        L.grid = std::min(A.total_tiles, ctx->sm_count);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ weights
+static bool dl_is_f32(const DLTensor& t) { return t.dtype.code == 2 && t.dtype.bits == 32 && t.dtype.lanes == 1; }
+static int64_t dl_numel(const DLTensor& t) { int64_t n = 1; for (int i = 0; i < t.ndim; ++i) n *= t.shape[i]; return n; }
+static bool dl_compact(const DLTensor& t) {
+    if (!t.strides) return true;
+    int64_t s = 1;
+    for (int i = t.ndim - 1; i >= 0; --i) { if (t.shape[i] != 1 && t.strides[i] != s) return false; s *= t.shape[i]; }
+    return true;
+}
+
+void Net::load(int n, const char* const* names, DLManagedTensor* const* tensors_in) {
+    cudaStream_t st = ctx->stream;
+    for (int i = 0; i < n; ++i) {
+        Y3_CHECK(names[i] && tensors_in[i], Y3_ERR_INVALID, "weight %d is NULL", i);
+        const std::string full(names[i]);
+        const size_t slash = full.find('/');
+        Y3_CHECK(slash != std::string::npos, Y3_ERR_INVALID, "weight name '%s' is not 'layer/variable'", names[i]);
+        std::string layer = full.substr(0, slash), var = full.substr(slash + 1);
+        const size_t colon = var.find(':');
+        if (colon != std::string::npos) var = var.substr(0, colon);       // "kernel:0"
+        const DLTensor& t = tensors_in[i]->dl_tensor;
+        Y3_CHECK(dl_is_f32(t) && dl_compact(t), Y3_ERR_INVALID, "weight '%s' must be compact float32", names[i]);
+        Y3_CHECK(t.device.device_type == kDLCPU || t.device.device_type == kDLCUDAHost || t.device.device_type == kDLCUDA,
+                 Y3_ERR_INVALID, "weight '%s': unsupported DLPack device %d", names[i], t.device.device_type);
+        const int64_t numel = dl_numel(t);
+        const void* src = static_cast<const char*>(t.data) + t.byte_offset;
+        Op* op = nullptr;
+        bool is_bn = false;
+        for (Op& o : ops) {
+            if (o.name == layer) { op = &o; break; }
+            if (o.bn == layer) { op = &o; is_bn = true; break; }
+        }
+        Y3_CHECK(op, Y3_ERR_INVALID, "weight '%s': no such layer in this network", names[i]);
+        stage.reserve((size_t)numel * 4);
+        const cudaMemcpyKind kind = t.device.device_type == kDLCUDA ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        const int taps = op->k * op->k;
+        if (is_bn) {
+            int slot = var == "gamma" ? 0 : var == "beta" ? 1 : var == "moving_mean" ? 2 : var == "moving_variance" ? 3 : -1;
+            Y3_CHECK(slot >= 0, Y3_ERR_INVALID, "weight '%s': unknown BatchNorm variable", names[i]);
+            Y3_CHECK(numel == op->cout, Y3_ERR_INVALID, "weight '%s': expected %d values, got %lld", names[i], op->cout, (long long)numel);
+            Y3_CUDA(cudaMemcpyAsync(op->bn_raw.as<float>() + (size_t)slot * op->cout_pad, src, (size_t)numel * 4, kind, st));
+            op->have |= (4u << slot);
+        } else if (var == "bias") {
+            Y3_CHECK(numel == op->cout, Y3_ERR_INVALID, "weight '%s': expected %d values, got %lld", names[i], op->cout, (long long)numel);
+            Y3_CUDA(cudaMemcpyAsync(op->bias.p, src, (size_t)numel * 4, kind, st));
+            op->have |= 2u;
+        } else if (var == "kernel") {
+            const int64_t expect = (int64_t)taps * op->cin * op->cout;
+            Y3_CHECK(numel == expect, Y3_ERR_INVALID, "weight '%s': expected %lld values ([%d,%d,%d,%d]), got %lld", names[i],
+                     (long long)expect, op->k, op->k, op->kind == Op::CONVT ? op->cout : op->cin,
+                     op->kind == Op::CONVT ? op->cin : op->cout, (long long)numel);
+            if (op->kind == Op::STEM) {
+                Y3_CUDA(cudaMemcpyAsync(op->w.p, src, (size_t)numel * 4, kind, st));
+            } else {
+                Y3_CUDA(cudaMemcpyAsync(stage.p, src, (size_t)numel * 4, kind, st));
+                if (op->kind == Op::CONVT) pack_convt_weight(ctx, stage.as<float>(), op->w.as<__nv_bfloat16>(), numel);
+                else pack_conv_weight(ctx, stage.as<float>(), op->w.as<__nv_bfloat16>(), taps, op->cin, op->cout, op->cout_pad);
+            }
+            op->have |= 1u;
+        } else {
+            fail(Y3_ERR_INVALID, "weight '%s': unknown variable", names[i]);
+        }
+        Y3_CUDA(cudaStreamSynchronize(st));       // the source may be released by its deleter
+    }
+    // fold BatchNorm, check completeness
+    loaded = true;
+    for (Op& op : ops) {
+        const bool needs_bn = (op.kind == Op::CONV || op.kind == Op::STEM);
+        const unsigned need = needs_bn ? 0x3fu : 0x3u;
+        if ((op.have & need) != need) { loaded = false; missing = op.name + (needs_bn ? " / " + op.bn : ""); continue; }
+        if (needs_bn) {
+            float* r = op.bn_raw.as<float>();
+            bn_fold(ctx, r, r + op.cout_pad, r + 2 * op.cout_pad, r + 3 * op.cout_pad, op.scale.as<float>(),
+                    op.shift.as<float>(), op.cout);
+        }
+    }
+    Y3_CUDA(cudaStreamSynchronize(st));
+    // ownership: the tensors are released only when the whole call succeeded (on failure the
+    // caller still owns them, so a DLPack capsule's own destructor stays valid)
+    for (int i = 0; i < n; ++i)
+        if (tensors_in[i]->deleter) tensors_in[i]->deleter(tensors_in[i]);
+}
+
+// ------------------------------------------------------------------------------------------ forward
+void Net::forward(const float* in_dev, int b) {
+    Y3_CHECK(loaded, Y3_ERR_STATE, "weights not (completely) loaded - missing %s", missing.c_str());
+    Y3_CHECK(b >= 1 && b <= maxB, Y3_ERR_INVALID, "batch %d outside 1..%d", b, maxB);
+    for (Op& op : ops) {
+        if (op.kind == Op::STEM) {
+            launch_stem(ctx, in_dev, reinterpret_cast<__nv_bfloat16*>(tensors[op.out.t].ptr), op.w.as<float>(),
+                        op.bias.as<float>(), op.scale.as<float>(), op.shift.as<float>(), b, H, W, C);
+            continue;
+        }
+        if (cur_batch != b) set_batch(op, b);
+        for (const ConvLaunch& L : op.launches) launch_conv(ctx, L);
+    }
+    cur_batch = b;
+}
+
+void Net::decode(int b) {
+    DecodeArgs D;
+    memset(&D, 0, sizeof(D));
+    for (int s = 0; s < 3; ++s) {
+        D.head[s] = head[s]; D.gh[s] = gh[s]; D.gw[s] = gw[s]; D.row_start[s] = row_start[s];
+        // np.asarray(img_size[0:2], float32) // np.asarray(grid_size, float32)   (model.py:127)
+        D.stride_h[s] = floorf((float)H / (float)gh[s]);
+        D.stride_w[s] = floorf((float)W / (float)gw[s]);
+    }
+    for (int a = 0; a < na; ++a) { D.anchor_w[a] = ctx->cfg.anchors[a][0]; D.anchor_h[a] = ctx->cfg.anchors[a][1]; }
+    D.na = na; D.nc = nc; D.pitch = HEAD_PITCH; D.n_total = (int)rows_per_image; D.batch = b;
+    launch_decode(ctx, D, boxes.as<float>());
+}
+
+Net::~Net() {
+    for (void* p : owned) cudaFree(p);
+}
+
+}  // namespace y3

@@ -1,0 +1,477 @@
+// nms.cu - confidence thresholding, warp-ballot stream compaction, (class,score) ordering and
+// exact greedy per-class NMS on the device.
+//
+// Reference behaviour reproduced bit for bit (fp32, NumPy operand order, no FMA contraction):
+//   filter_small_boxes  bbox_utils.py:274-281   (w > min) & (h > min), strict
+//   per_class_nms       bbox_utils.py:240-271   score = sqrt(cls*obj) >= float32(thr), class-major output
+//   single_class_nms    bbox_utils.py:217-237   greedy, survivors are (iou <= thr); NaN => suppressed
+//   compute_iou         bbox_utils.py:200-214
+// Ordering rule: score descending, then input row ascending (the reference's argsort()[::-1] is
+// unpinned on ties - SURVEY.md Q11 - this is the one documented deviation).
+//
+// Pipeline (all on ctx->stream):
+//   k_candidates      one thread per (row, class): threshold, ballot-compact, emit a 64-bit key
+//                     [segment | ~orderable(score) | row] and the global row as the value
+//   radix sort        cub::DeviceRadixSort on the used key bits only (toolkit primitive)
+//   k_gather_sorted   boxes / areas of the sorted candidates as SoA (coalesced for the sweeps)
+//   k_seg_offsets     segment (= image x class) boundaries by binary search on the sorted keys
+//   k_nms_segments    one CTA per segment: per 512-box chunk a shared-memory IoU bitmask
+//                     (512 x 8 u64), a serial suppression sweep over it, then the chunk's kept
+//                     boxes are applied to the rest of the segment
+//   k_nms_resolve / k_nms_apply   the same two phases as separate launches for very large
+//                     segments, so that the apply phase uses the whole GPU
+//   k_count / k_scan / k_scatter  ordered compaction of the keep flags into the output arrays
+// The n x n/64 bitmask is never materialised in HBM.
+#include "postproc.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+namespace y3 {
+
+static constexpr int NMS_T = 512;             // boxes per chunk
+static constexpr int NMS_W = NMS_T / 64;      // mask words per row
+static constexpr int NMS_THREADS = 256;
+static constexpr int64_t BIG_SEGMENT = 8192;  // segments above this use resolve/apply launches
+
+// ------------------------------------------------------------------------------------------
+// orderable score bits: ascending unsigned order == ascending float order
+__device__ __forceinline__ uint32_t orderable(float s) {
+    const uint32_t u = __float_as_uint(s);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_orderable(uint32_t o) {
+    const uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+    return __uint_as_float(u);
+}
+
+struct KeyLayout {
+    int row_bits, seg_shift, total_bits;
+    uint64_t row_mask;
+};
+
+__global__ void __launch_bounds__(256)
+k_candidates(CandSource src, KeyLayout kl, int64_t total, uint64_t* __restrict__ keys,
+             uint32_t* __restrict__ vals, unsigned long long* __restrict__ counter, int64_t cap) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    // total is rounded up to a multiple of 32 by the loop bound so that ballots stay converged
+    const int64_t total_r = (total + 31) & ~(int64_t)31;
+    const float thr = src.score_thr;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total_r; e += stride) {
+        bool pass = false;
+        uint64_t key = 0;
+        uint32_t val = 0;
+        if (e < total) {
+            const int64_t grow = e / src.nc;                 // global row = img * rows + row
+            const int c = (int)(e - grow * src.nc);
+            const float p = __ldg(src.cls + grow * src.cls_stride + c);
+            float s;
+            if (src.raw_scores) {
+                s = p;
+                pass = true;
+            } else {
+                const float o = src.obj ? __ldg(src.obj + grow * src.obj_stride) : 1.0f;
+                s = __fsqrt_rn(__fmul_rn(p, o));             // np.sqrt(class_probs * objectness)
+                pass = (s >= thr);                           // NaN -> false
+            }
+            if (pass && src.filter_small) {
+                const float* b = src.box + grow * src.box_stride;
+                const float w = __fsub_rn(__ldg(b + 2), __ldg(b + 0));
+                const float h = __fsub_rn(__ldg(b + 3), __ldg(b + 1));
+                pass = (w > src.min_size) && (h > src.min_size);
+            }
+            if (pass) {
+                const int64_t img = grow / src.rows_per_image;
+                const int64_t row = grow - img * src.rows_per_image;
+                const uint64_t seg = (uint64_t)(img * src.nc + c);
+                key = (seg << kl.seg_shift) | ((uint64_t)(~orderable(s)) << kl.row_bits) | (uint64_t)row;
+                val = (uint32_t)grow;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            unsigned long long base = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (pass) {
+                const int64_t pos = (int64_t)base + __popc(m & ((1u << lane) - 1u));
+                if (pos < cap) { keys[pos] = key; vals[pos] = val; }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_sorted(CandSource src, const uint32_t* __restrict__ vals, int64_t n, float4* __restrict__ sbox,
+                float* __restrict__ sarea, uint8_t* __restrict__ supp, uint8_t* __restrict__ keepf) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float* b = src.box + (int64_t)vals[p] * src.box_stride;
+    const float4 bx = make_float4(__ldg(b), __ldg(b + 1), __ldg(b + 2), __ldg(b + 3));
+    sbox[p] = bx;
+    sarea[p] = box_area_exact(bx);
+    supp[p] = 0;
+    keepf[p] = 0;
+}
+
+__global__ void k_seg_offsets(const uint64_t* __restrict__ keys, int64_t n, int seg_shift, int nseg,
+                              int64_t* __restrict__ off) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > nseg) return;
+    int64_t lo = 0, hi = n;                     // first p with seg(key[p]) >= s
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((keys[mid] >> seg_shift) < (uint64_t)s) lo = mid + 1; else hi = mid;
+    }
+    off[s] = lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// One chunk (<= NMS_T boxes starting at `base`) of one segment: build the IoU bitmask in shared
+// memory, sweep it serially, return the kept local indices in s_klist / s_nk.
+struct ChunkSmem {
+    float4 box[NMS_T];
+    float area[NMS_T];
+    unsigned long long mask[NMS_T * NMS_W];
+    unsigned long long dead[NMS_W];
+    int klist[NMS_T];
+    int nk;
+};
+
+__device__ __forceinline__ void chunk_resolve(ChunkSmem& S, const float4* __restrict__ sbox,
+                                              const float* __restrict__ sarea,
+                                              const uint8_t* __restrict__ supp, int64_t base, int ct, float thr) {
+    const int tid = threadIdx.x;
+    // load + dead bits (already suppressed by earlier chunks, or past the end)
+    uint32_t* dead32 = reinterpret_cast<uint32_t*>(S.dead);
+    for (int j = tid; j < NMS_T; j += NMS_THREADS) {
+        bool dead = true;
+        if (j < ct) {
+            S.box[j] = sbox[base + j];
+            S.area[j] = sarea[base + j];
+            dead = supp[base + j] != 0;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, dead);
+        if ((tid & 31) == 0) dead32[j >> 5] = b;
+    }
+    __syncthreads();
+    // bitmask: lanes walk rows i, all lanes of a warp share the word w => box j is a broadcast read
+    const int nw = (ct + 63) >> 6;
+    for (int idx = tid; idx < NMS_T * nw; idx += NMS_THREADS) {
+        const int w = idx / NMS_T;
+        const int i = idx - w * NMS_T;
+        if (i >= ct || w < (i >> 6)) continue;
+        if ((S.dead[i >> 6] >> (i & 63)) & 1ull) continue;          // row never read by the sweep
+        const float4 bi = S.box[i];
+        const float ai = S.area[i];
+        unsigned long long bits = 0;
+        const int j0 = w << 6;
+        const int jn = min(64, ct - j0);
+        for (int b = 0; b < jn; ++b) {
+            const int j = j0 + b;
+            const float iou = iou_exact(bi, ai, S.box[j], S.area[j]);
+            if (j > i && !(iou <= thr)) bits |= (1ull << b);
+        }
+        S.mask[i * NMS_W + w] = bits;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long dead[NMS_W];
+#pragma unroll
+        for (int w = 0; w < NMS_W; ++w) dead[w] = S.dead[w];
+        int nk = 0;
+#pragma unroll
+        for (int w0 = 0; w0 < NMS_W; ++w0) {
+            unsigned long long cur = ~dead[w0];
+            while (cur) {
+                const int b = __ffsll((long long)cur) - 1;
+                const int i = (w0 << 6) + b;
+                S.klist[nk++] = i;
+                const unsigned long long* row = S.mask + i * NMS_W;
+#pragma unroll
+                for (int w = 0; w < NMS_W; ++w)
+                    if (w >= w0) dead[w] |= row[w];
+                const unsigned long long above = (b == 63) ? 0ull : (~0ull << (b + 1));
+                cur = ~dead[w0] & above;
+            }
+        }
+        S.nk = nk;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(NMS_THREADS)
+k_nms_segments(const float4* __restrict__ sbox, const float* __restrict__ sarea, uint8_t* __restrict__ supp,
+               uint8_t* __restrict__ keepf, const int64_t* __restrict__ seg_off, int nseg, float thr,
+               int64_t big_segment) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ChunkSmem& S = *reinterpret_cast<ChunkSmem*>(smem_raw);
+    for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+        const int64_t s0 = seg_off[seg];
+        const int64_t m = seg_off[seg + 1] - s0;
+        if (m <= 0 || m > big_segment) continue;
+        for (int64_t c0 = 0; c0 < m; c0 += NMS_T) {
+            const int ct = (int)min((int64_t)NMS_T, m - c0);
+            chunk_resolve(S, sbox, sarea, supp, s0 + c0, ct, thr);
+            const int nk = S.nk;
+            for (int t = threadIdx.x; t < nk; t += NMS_THREADS) keepf[s0 + c0 + S.klist[t]] = 1;
+            // apply this chunk's kept boxes to the rest of the segment
+            for (int64_t j = c0 + ct + threadIdx.x; j < m; j += NMS_THREADS) {
+                if (supp[s0 + j]) continue;
+                const float4 bj = sbox[s0 + j];
+                const float aj = sarea[s0 + j];
+                for (int t = 0; t < nk; ++t) {
+                    const int k = S.klist[t];
+                    const float iou = iou_exact(S.box[k], S.area[k], bj, aj);
+                    if (!(iou <= thr)) { supp[s0 + j] = 1; break; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// big-segment path: resolve one chunk on one CTA, publish its kept boxes...
+__global__ void __launch_bounds__(NMS_THREADS)
+k_nms_resolve(const float4* __restrict__ sbox, const float* __restrict__ sarea, const uint8_t* __restrict__ supp,
+              uint8_t* __restrict__ keepf, int64_t base, int ct, float thr, float4* __restrict__ kbox,
+              float* __restrict__ karea, int* __restrict__ knum) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ChunkSmem& S = *reinterpret_cast<ChunkSmem*>(smem_raw);
+    chunk_resolve(S, sbox, sarea, supp, base, ct, thr);
+    const int nk = S.nk;
+    for (int t = threadIdx.x; t < nk; t += NMS_THREADS) {
+        const int k = S.klist[t];
+        keepf[base + k] = 1;
+        kbox[t] = S.box[k];
+        karea[t] = S.area[k];
+    }
+    if (threadIdx.x == 0) *knum = nk;
+}
+
+// ...and apply them to every later box of the segment with the whole GPU.
+__global__ void __launch_bounds__(256)
+k_nms_apply(const float4* __restrict__ sbox, const float* __restrict__ sarea, uint8_t* __restrict__ supp,
+            int64_t first, int64_t last, float thr, const float4* __restrict__ kbox,
+            const float* __restrict__ karea, const int* __restrict__ knum) {
+    __shared__ float4 s_box[NMS_T];
+    __shared__ float s_area[NMS_T];
+    const int nk = *knum;
+    for (int t = threadIdx.x; t < nk; t += blockDim.x) { s_box[t] = kbox[t]; s_area[t] = karea[t]; }
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < last; j += stride) {
+        if (supp[j]) continue;
+        const float4 bj = sbox[j];
+        const float aj = sarea[j];
+        for (int t = 0; t < nk; ++t) {
+            const float iou = iou_exact(s_box[t], s_area[t], bj, aj);
+            if (!(iou <= thr)) { supp[j] = 1; break; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// ordered compaction of keep flags
+__global__ void __launch_bounds__(CMP_BLOCK)
+k_count(const uint8_t* __restrict__ flags, int64_t n, int* __restrict__ blk) {
+    __shared__ int s_w[CMP_BLOCK / 32];
+    const int64_t p = (int64_t)blockIdx.x * CMP_BLOCK + threadIdx.x;
+    const bool f = p < n && flags[p];
+    const unsigned b = __ballot_sync(0xffffffffu, f);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = __popc(b);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = s_w[threadIdx.x];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) blk[blockIdx.x] = v;
+    }
+}
+
+// single block exclusive scan of nb block counts; total -> *total_out
+__global__ void __launch_bounds__(1024)
+k_scan(int* __restrict__ blk, int nb, long long* __restrict__ total_out) {
+    __shared__ long long s_part[1024];
+    const int per = (nb + 1023) / 1024;
+    const int b0 = threadIdx.x * per;
+    long long sum = 0;
+    for (int i = 0; i < per; ++i) if (b0 + i < nb) sum += blk[b0 + i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {            // Hillis-Steele inclusive scan
+        long long v = (threadIdx.x >= o) ? s_part[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    long long run = s_part[threadIdx.x] - sum;      // exclusive prefix of this thread's span
+    for (int i = 0; i < per; ++i) {
+        if (b0 + i < nb) { const int c = blk[b0 + i]; blk[b0 + i] = (int)run; run += c; }
+    }
+    if (threadIdx.x == 1023) *total_out = s_part[1023];
+}
+
+__global__ void __launch_bounds__(CMP_BLOCK)
+k_scatter(const uint8_t* __restrict__ flags, int64_t n, const int* __restrict__ blk,
+          const uint64_t* __restrict__ keys, const float4* __restrict__ sbox, KeyLayout kl, int nc,
+          float4* __restrict__ o_box, float* __restrict__ o_score, int32_t* __restrict__ o_label,
+          int32_t* __restrict__ o_img, int32_t* __restrict__ o_src) {
+    __shared__ int s_w[CMP_BLOCK / 32];
+    const int64_t p = (int64_t)blockIdx.x * CMP_BLOCK + threadIdx.x;
+    const bool f = p < n && flags[p];
+    const int rank = block_rank(f, s_w);
+    if (f) {
+        const int64_t q = (int64_t)blk[blockIdx.x] + rank;
+        const uint64_t key = keys[p];
+        const uint64_t seg = key >> kl.seg_shift;
+        o_box[q] = sbox[p];
+        o_score[q] = from_orderable(~(uint32_t)(key >> kl.row_bits));
+        o_label[q] = (int32_t)(seg % (uint64_t)nc);
+        o_img[q] = (int32_t)(seg / (uint64_t)nc);
+        o_src[q] = (int32_t)(key & kl.row_mask);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+int64_t PostProc::flag_offsets(const uint8_t* flags, int64_t n) {
+    cudaStream_t st = ctx->stream;
+    if (n <= 0) return 0;
+    const int nb = ceil_div(n, CMP_BLOCK);
+    blk.reserve((size_t)nb * 4);
+    counters.reserve(64);
+    host_small.reserve(64);
+    k_count<<<nb, CMP_BLOCK, 0, st>>>(flags, n, blk.as<int>());
+    Y3_LAUNCHED(ctx);
+    k_scan<<<1, 1024, 0, st>>>(blk.as<int>(), nb, reinterpret_cast<long long*>(counters.as<unsigned char>() + 8));
+    Y3_LAUNCHED(ctx);
+    unsigned long long* h = host_small.as<unsigned long long>();
+    Y3_CUDA(cudaMemcpyAsync(h + 1, counters.as<unsigned char>() + 8, 8, cudaMemcpyDeviceToHost, st));
+    Y3_CUDA(cudaStreamSynchronize(st));
+    return (int64_t)h[1];
+}
+
+NmsResult PostProc::run(const CandSource& src, float iou_thr) {
+    cudaStream_t st = ctx->stream;
+    NmsResult R;
+    const int64_t rows = src.rows_per_image * src.n_images;
+    const int64_t total = rows * src.nc;
+    if (total <= 0) return R;
+    const int64_t nseg64 = (int64_t)src.n_images * src.nc;
+    Y3_CHECK(rows < (1ll << 32), Y3_ERR_UNSUPPORTED, "too many rows (%lld)", (long long)rows);
+    KeyLayout kl;
+    kl.row_bits = ilog2_ceil((uint64_t)src.rows_per_image);
+    if (kl.row_bits == 0) kl.row_bits = 1;
+    kl.seg_shift = kl.row_bits + 32;
+    const int seg_bits = ilog2_ceil((uint64_t)nseg64 + 1);
+    kl.total_bits = kl.seg_shift + seg_bits;
+    kl.row_mask = (1ull << kl.row_bits) - 1ull;
+    Y3_CHECK(kl.total_bits <= 64, Y3_ERR_UNSUPPORTED, "sort key needs %d bits", kl.total_bits);
+    const int nseg = (int)nseg64;
+
+    int64_t cap = ctx->cfg.max_candidates > 0 ? ctx->cfg.max_candidates : total;
+    if (cap > total) cap = total;
+    keys[0].reserve(cap * 8); keys[1].reserve(cap * 8);
+    vals[0].reserve(cap * 4); vals[1].reserve(cap * 4);
+    counters.reserve(64);
+    host_small.reserve(64 + (size_t)(nseg + 1) * 8);
+    Y3_CUDA(cudaMemsetAsync(counters.p, 0, 64, st));
+
+    {
+        const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
+        k_candidates<<<blocks, 256, 0, st>>>(src, kl, total, keys[0].as<uint64_t>(), vals[0].as<uint32_t>(),
+                                             counters.as<unsigned long long>(), cap);
+        Y3_LAUNCHED(ctx);
+    }
+    unsigned long long* h_cnt = host_small.as<unsigned long long>();
+    Y3_CUDA(cudaMemcpyAsync(h_cnt, counters.p, 8, cudaMemcpyDeviceToHost, st));
+    Y3_CUDA(cudaStreamSynchronize(st));
+    const int64_t K = (int64_t)h_cnt[0];
+    R.n_cand = K;
+    Y3_CHECK(K <= cap, Y3_ERR_NOSPACE, "candidate list overflow: %lld candidates, capacity %lld "
+             "(raise y3_config.max_candidates)", (long long)K, (long long)cap);
+    if (K == 0) return R;
+
+    // sort by (segment, score desc, row asc)
+    size_t tmp_bytes = 0;
+    Y3_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys[0].as<uint64_t>(), keys[1].as<uint64_t>(),
+                                            vals[0].as<uint32_t>(), vals[1].as<uint32_t>(), K, 0, kl.total_bits, st));
+    sort_tmp.reserve(tmp_bytes);
+    Y3_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp.p, tmp_bytes, keys[0].as<uint64_t>(), keys[1].as<uint64_t>(),
+                                            vals[0].as<uint32_t>(), vals[1].as<uint32_t>(), K, 0, kl.total_bits, st));
+    count_launch(ctx, 2 * ((kl.total_bits + 7) / 8) + 1);
+    const uint64_t* skeys = keys[1].as<uint64_t>();
+    const uint32_t* svals = vals[1].as<uint32_t>();
+
+    sbox.reserve(K * 16); sarea.reserve(K * 4); supp.reserve(K); keepf.reserve(K);
+    seg_off.reserve((size_t)(nseg + 1) * 8);
+    k_gather_sorted<<<ceil_div(K, 256), 256, 0, st>>>(src, svals, K, sbox.as<float4>(), sarea.as<float>(),
+                                                      supp.as<uint8_t>(), keepf.as<uint8_t>());
+    Y3_LAUNCHED(ctx);
+    k_seg_offsets<<<ceil_div(nseg + 1, 256), 256, 0, st>>>(skeys, K, kl.seg_shift, nseg, seg_off.as<int64_t>());
+    Y3_LAUNCHED(ctx);
+
+    // segment sizes are needed on the host only to route very large segments
+    int64_t* h_off = reinterpret_cast<int64_t*>(host_small.as<unsigned char>() + 64);
+    bool any_big = false, any_small = false;
+    if (K > BIG_SEGMENT) {
+        Y3_CUDA(cudaMemcpyAsync(h_off, seg_off.p, (size_t)(nseg + 1) * 8, cudaMemcpyDeviceToHost, st));
+        Y3_CUDA(cudaStreamSynchronize(st));
+        for (int s = 0; s < nseg; ++s) {
+            const int64_t m = h_off[s + 1] - h_off[s];
+            if (m > BIG_SEGMENT) any_big = true; else if (m > 0) any_small = true;
+        }
+    } else {
+        any_small = true;
+    }
+
+    const size_t smem = sizeof(ChunkSmem);
+    static_assert(sizeof(ChunkSmem) <= 48 * 1024, "ChunkSmem must fit the default dynamic smem limit");
+    if (any_small) {
+        const int blocks = std::min(nseg, ctx->sm_count * 4);
+        k_nms_segments<<<blocks, NMS_THREADS, smem, st>>>(sbox.as<float4>(), sarea.as<float>(), supp.as<uint8_t>(),
+                                                          keepf.as<uint8_t>(), seg_off.as<int64_t>(), nseg, iou_thr,
+                                                          BIG_SEGMENT);
+        Y3_LAUNCHED(ctx);
+    }
+    if (any_big) {
+        kbuf.reserve((size_t)NMS_T * 20 + 16);
+        float4* kbox = kbuf.as<float4>();
+        float* karea = reinterpret_cast<float*>(kbuf.as<unsigned char>() + (size_t)NMS_T * 16);
+        int* knum = reinterpret_cast<int*>(kbuf.as<unsigned char>() + (size_t)NMS_T * 20);
+        for (int s = 0; s < nseg; ++s) {
+            const int64_t s0 = h_off[s], m = h_off[s + 1] - h_off[s];
+            if (m <= BIG_SEGMENT) continue;
+            for (int64_t c0 = 0; c0 < m; c0 += NMS_T) {
+                const int ct = (int)std::min<int64_t>(NMS_T, m - c0);
+                k_nms_resolve<<<1, NMS_THREADS, smem, st>>>(sbox.as<float4>(), sarea.as<float>(), supp.as<uint8_t>(),
+                                                            keepf.as<uint8_t>(), s0 + c0, ct, iou_thr, kbox, karea, knum);
+                Y3_LAUNCHED(ctx);
+                const int64_t first = s0 + c0 + ct, last = s0 + m;
+                if (first < last) {
+                    const int blocks = (int)std::min<int64_t>((last - first + 255) / 256, (int64_t)ctx->sm_count * 8);
+                    k_nms_apply<<<blocks, 256, 0, st>>>(sbox.as<float4>(), sarea.as<float>(), supp.as<uint8_t>(),
+                                                        first, last, iou_thr, kbox, karea, knum);
+                    Y3_LAUNCHED(ctx);
+                }
+            }
+        }
+    }
+
+    // ordered compaction of the kept candidates
+    const int nb = ceil_div(K, CMP_BLOCK);
+    const int64_t kept = flag_offsets(keepf.as<uint8_t>(), K);
+    R.n_kept = kept;
+    if (kept == 0) return R;
+    o_box.reserve(kept * 16); o_score.reserve(kept * 4); o_label.reserve(kept * 4);
+    o_img.reserve(kept * 4); o_src.reserve(kept * 4);
+    k_scatter<<<nb, CMP_BLOCK, 0, st>>>(keepf.as<uint8_t>(), K, blk.as<int>(), skeys, sbox.as<float4>(), kl, src.nc,
+                                        o_box.as<float4>(), o_score.as<float>(), o_label.as<int32_t>(),
+                                        o_img.as<int32_t>(), o_src.as<int32_t>());
+    Y3_LAUNCHED(ctx);
+    R.boxes = o_box.as<float4>(); R.scores = o_score.as<float>(); R.labels = o_label.as<int32_t>();
+    R.img = o_img.as<int32_t>(); R.src_row = o_src.as<int32_t>();
+    return R;
+}
+
+}  // namespace y3

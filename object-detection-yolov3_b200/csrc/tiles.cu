@@ -1,0 +1,199 @@
+// tiles.cu - tile slicing + per-tile normalisation (front-end) and seam stitching (back-end) of
+// inference_tiled.py on the device.
+//
+// Front-end  (inference_tiled.py:29-100, 202-212; imagereader.py:34-46)
+//   tile grid: zone = tile - 2r, tiles start every `zone` pixels, crop [i-r, i+zone+r) clamped to the
+//   image and np.pad(mode='reflect') back to the tile size; r = 0 on an axis whose tile covers the
+//   image.  The RECORDED origin is the clamped one (SURVEY Q12 - border tiles are shifted by +r; kept).
+//   Each tile is z-scored with its own mean / population std over all channels (Q14); std <= 1 means
+//   "subtract the mean only".  One CTA per tile: two-pass fp64 statistics (mean, then sum of squared
+//   deviations), then a third pass writes (x - mean) / std as NCHW fp32.  The image stays resident in
+//   HBM in its source dtype; the reflect is index arithmetic, no padded copy is ever made.
+// Back-end   (inference_tiled.py:235-301)
+//   ghost-band ownership by box centre, origin add (fp32), np.round (half-to-even) -> int32,
+//   centre-inside-image filter, clamp to [0, size-1]; ordered compaction keeps the reference's order.
+#include "tiles.cuh"
+
+namespace y3 {
+
+std::vector<TileGeo> plan_tiles(int64_t H, int64_t W, int th, int tw, int edge, int* ry_out, int* rx_out) {
+    Y3_CHECK(th > 0 && tw > 0 && th % 32 == 0 && tw % 32 == 0, Y3_ERR_INVALID, "tile size %dx%d must be a multiple of 32", th, tw);
+    Y3_CHECK(edge >= 0 && edge % 32 == 0, Y3_ERR_INVALID, "edge range %d must be a multiple of 32", edge);
+    const int ry = th >= H ? 0 : edge, rx = tw >= W ? 0 : edge;
+    const int zy = th - 2 * ry, zx = tw - 2 * rx;
+    Y3_CHECK(zy > 0 && zx > 0, Y3_ERR_INVALID, "tile %dx%d leaves no zone of responsibility with edge range %d", th, tw, edge);
+    std::vector<TileGeo> v;
+    for (int64_t i = 0; i < H; i += zy)
+        for (int64_t j = 0; j < W; j += zx) {
+            TileGeo g;
+            int64_t ys = i - ry, ye = i + zy + ry, xs = j - rx, xe = j + zx + rx;
+            g.pre_y = ys < 0 ? (int)-ys : 0;
+            g.pre_x = xs < 0 ? (int)-xs : 0;
+            g.y0 = (int)std::max<int64_t>(ys, 0); g.x0 = (int)std::max<int64_t>(xs, 0);
+            g.y1 = (int)std::min<int64_t>(ye, H); g.x1 = (int)std::min<int64_t>(xe, W);
+            g.rec_x = g.x0; g.rec_y = g.y0;
+            v.push_back(g);
+        }
+    if (ry_out) *ry_out = ry;
+    if (rx_out) *rx_out = rx;
+    return v;
+}
+
+// np.pad(mode='reflect') index: q relative to the crop start, n = crop length
+__device__ __forceinline__ int reflect_idx(int q, int n) {
+    if (n == 1) return 0;
+    const int period = 2 * (n - 1);
+    q %= period;
+    if (q < 0) q += period;
+    return q < n ? q : period - q;
+}
+
+template <typename T>
+__device__ __forceinline__ float load_px(const void* img, long long idx) { return (float)reinterpret_cast<const T*>(img)[idx]; }
+
+__device__ __forceinline__ float load_any(const void* img, int dtype, long long idx) {
+    switch (dtype) {
+        case Y3_U8: return load_px<uint8_t>(img, idx);
+        case Y3_U16: return load_px<uint16_t>(img, idx);
+        case Y3_I32: return load_px<int32_t>(img, idx);
+        default: return load_px<float>(img, idx);
+    }
+}
+
+__device__ __forceinline__ double block_sum(double v, double* s_red) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_red[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        double t = lane < (int)(blockDim.x >> 5) ? s_red[lane] : 0.0;
+        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) s_red[32] = t;
+    }
+    __syncthreads();
+    return s_red[32];
+}
+
+__global__ void __launch_bounds__(1024)
+k_tile_norm(const void* __restrict__ img, int dtype, long long row_lo, int W, int C, const TileGeo* __restrict__ geo,
+            int th, int tw, float* __restrict__ out, float* __restrict__ stats) {
+    __shared__ double s_red[33];
+    const TileGeo g = geo[blockIdx.x];
+    const int ny = g.y1 - g.y0, nx = g.x1 - g.x0;
+    const int n_el = th * tw * C;
+    // element e -> (c, ty, tx) with tx fastest (coalesced NCHW writes)
+    auto fetch = [&](int e) -> float {
+        const int tx = e % tw;
+        const int r = e / tw;
+        const int ty = r % th;
+        const int c = r / th;
+        const int sy = g.y0 + reflect_idx(ty - g.pre_y, ny);
+        const int sx = g.x0 + reflect_idx(tx - g.pre_x, nx);
+        return load_any(img, dtype, ((long long)(sy - row_lo) * W + sx) * C + c);
+    };
+    double acc = 0.0;
+    for (int e = threadIdx.x; e < n_el; e += blockDim.x) acc += (double)fetch(e);
+    const double mean = block_sum(acc, s_red) / (double)n_el;
+    acc = 0.0;
+    for (int e = threadIdx.x; e < n_el; e += blockDim.x) { const double d = (double)fetch(e) - mean; acc += d * d; }
+    const double var = block_sum(acc, s_red) / (double)n_el;
+    const float mu = (float)mean;
+    const float sd = (float)sqrt(var);
+    float* o = out + (long long)blockIdx.x * n_el;
+    if (sd <= 1.0f) {
+        for (int e = threadIdx.x; e < n_el; e += blockDim.x) o[e] = __fsub_rn(fetch(e), mu);
+    } else {
+        for (int e = threadIdx.x; e < n_el; e += blockDim.x) o[e] = __fdiv_rn(__fsub_rn(fetch(e), mu), sd);
+    }
+    if (stats && threadIdx.x == 0) { stats[2 * blockIdx.x] = mu; stats[2 * blockIdx.x + 1] = sd; }
+}
+
+void launch_tile_norm(y3_context* ctx, const void* img_dev, int dtype, long long row_lo, int W, int C,
+                      const TileGeo* geo_dev, int count, int th, int tw, float* out, float* stats) {
+    if (count <= 0) return;
+    k_tile_norm<<<count, 1024, 0, ctx->stream>>>(img_dev, dtype, row_lo, W, C, geo_dev, th, tw, out, stats);
+    Y3_LAUNCHED(ctx);
+}
+
+// ------------------------------------------------------------------------------------------ stitch
+__global__ void __launch_bounds__(256)
+k_stitch_flags(const float4* __restrict__ boxes, const int32_t* __restrict__ tile, int64_t n,
+               const TileGeo* __restrict__ geo, StitchArgs S, int4* __restrict__ ibox, uint8_t* __restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 b = boxes[i];
+    const TileGeo g = geo[tile[i]];
+    const float r = (float)S.edge;
+    const float ox = (float)g.rec_x, oy = (float)g.rec_y;
+    // inference_tiled.py:237-254 (fp32 scalars, python-int operands converted to fp32)
+    const float cx = __fdiv_rn(__fadd_rn(b.z, b.x), 2.0f);
+    const float cy = __fdiv_rn(__fadd_rn(b.w, b.y), 2.0f);
+    const float gx = __fadd_rn(cx, ox);
+    const float gy = __fadd_rn(cy, oy);
+    bool bad = (gy > r) && (cy < r);
+    bad |= (gy <= (float)(S.img_h - S.edge)) && (cy >= (float)(S.tile_h - S.edge));
+    bad |= (gx > r) && (cx < r);
+    bad |= (gx <= (float)(S.img_w - S.edge)) && (cx >= (float)(S.tile_w - S.edge));
+    // :263-266 origin add, :278 np.round -> int32
+    int x0 = (int)rintf(__fadd_rn(b.x, ox));
+    int y0 = (int)rintf(__fadd_rn(b.y, oy));
+    int x1 = (int)rintf(__fadd_rn(b.z, ox));
+    int y1 = (int)rintf(__fadd_rn(b.w, oy));
+    // :281-288 centre must lie inside the image (int32 sum, then / 2.0 in double)
+    const double ccx = (double)(x1 + x0) / 2.0, ccy = (double)(y1 + y0) / 2.0;
+    const bool outside = (ccx < 0) || (ccx >= (double)S.img_w) || (ccy < 0) || (ccy >= (double)S.img_h);
+    // :291-301 clamp
+    const int mw = (int)S.img_w - 1, mh = (int)S.img_h - 1;
+    x0 = min(max(x0, 0), mw); x1 = min(max(x1, 0), mw);
+    y0 = min(max(y0, 0), mh); y1 = min(max(y1, 0), mh);
+    ibox[i] = make_int4(x0, y0, x1, y1);
+    flags[i] = (!bad && !outside) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(CMP_BLOCK)
+k_stitch_scatter(const uint8_t* __restrict__ flags, int64_t n, const int* __restrict__ blk, const int4* __restrict__ ibox,
+                 const float* __restrict__ scores, const int32_t* __restrict__ labels, double* __restrict__ preds) {
+    __shared__ int s_w[CMP_BLOCK / 32];
+    const int64_t p = (int64_t)blockIdx.x * CMP_BLOCK + threadIdx.x;
+    const bool f = p < n && flags[p];
+    const int rank = block_rank(f, s_w);
+    if (f) {
+        double* o = preds + ((int64_t)blk[blockIdx.x] + rank) * 6;
+        const int4 b = ibox[p];
+        o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w;
+        o[4] = (double)scores[p];
+        o[5] = (double)labels[p];
+    }
+}
+
+int64_t Tiler::stitch(PostProc* post, const NmsResult& R, const TileGeo* geo_dev, const StitchArgs& S) {
+    if (R.n_kept <= 0) return 0;
+    cudaStream_t st = ctx->stream;
+    ibox.reserve((size_t)R.n_kept * 16);
+    flags.reserve((size_t)R.n_kept);
+    k_stitch_flags<<<ceil_div(R.n_kept, 256), 256, 0, st>>>(R.boxes, R.img, R.n_kept, geo_dev, S, ibox.as<int4>(),
+                                                           flags.as<uint8_t>());
+    Y3_LAUNCHED(ctx);
+    const int64_t total = post->flag_offsets(flags.as<uint8_t>(), R.n_kept);
+    if (total == 0) return 0;
+    // grow the accumulator, preserving what earlier tile batches produced
+    const size_t need = (size_t)(acc_rows + total) * 48;
+    if (need > acc.cap) {
+        DevBuf bigger;
+        bigger.reserve(std::max(need, acc.cap * 2));
+        if (acc_rows) Y3_CUDA(cudaMemcpyAsync(bigger.p, acc.p, (size_t)acc_rows * 48, cudaMemcpyDeviceToDevice, st));
+        Y3_CUDA(cudaStreamSynchronize(st));
+        acc.release();
+        acc.p = bigger.p; acc.cap = bigger.cap;
+        bigger.p = nullptr; bigger.cap = 0;
+    }
+    k_stitch_scatter<<<ceil_div(R.n_kept, CMP_BLOCK), CMP_BLOCK, 0, st>>>(flags.as<uint8_t>(), R.n_kept, post->blk.as<int>(),
+                                                                         ibox.as<int4>(), R.scores, R.labels,
+                                                                         acc.as<double>() + acc_rows * 6);
+    Y3_LAUNCHED(ctx);
+    acc_rows += total;
+    return total;
+}
+
+}  // namespace y3

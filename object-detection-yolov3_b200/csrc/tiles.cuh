@@ -1,0 +1,33 @@
+// tiles.cuh - tile geometry + front-end / back-end launchers (see tiles.cu).
+#pragma once
+#include "common.cuh"
+#include "postproc.cuh"
+
+namespace y3 {
+
+struct TileGeo {
+    int y0, y1, x0, x1;     // clamped crop in the image
+    int pre_y, pre_x;       // reflect padding before the crop
+    int rec_x, rec_y;       // origin the reference records (clamped)
+};
+
+struct StitchArgs {
+    int64_t img_h, img_w;
+    int tile_h, tile_w, edge;
+};
+
+std::vector<TileGeo> plan_tiles(int64_t H, int64_t W, int th, int tw, int edge, int* ry, int* rx);
+
+void launch_tile_norm(y3_context* ctx, const void* img_dev, int dtype, long long row_lo, int W, int C,
+                      const TileGeo* geo_dev, int count, int th, int tw, float* out, float* stats);
+
+struct Tiler {
+    y3_context* ctx;
+    DevBuf geo, img, tiles, ibox, flags, acc, dets;
+    int64_t acc_rows = 0;
+    explicit Tiler(y3_context* c) : ctx(c) {}
+    // appends the surviving boxes of R (image index = tile index inside geo_dev) to acc; returns how many
+    int64_t stitch(PostProc* post, const NmsResult& R, const TileGeo* geo_dev, const StitchArgs& S);
+};
+
+}  // namespace y3

@@ -1,0 +1,296 @@
+"""Host-side wrapper of one y3_handle: construction, DLPack weight hand-over, forward / detect /
+tiled inference.  Pure plumbing - all arithmetic happens in libyolo3_b200.so on the GPU."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import MEM_DEVICE, MEM_HOST, Y3Config, Y3Timings, check
+
+DEFAULT_ANCHORS = [(32, 32), (128, 128), (256, 256)]          # model.py:433
+_DTYPES = {np.dtype(np.uint8): _lib.U8, np.dtype(np.uint16): _lib.U16, np.dtype(np.int32): _lib.I32,
+           np.dtype(np.float32): _lib.F32}
+_USED = b"used_dltensor"
+
+_PyCapsule_GetPointer = ctypes.pythonapi.PyCapsule_GetPointer
+_PyCapsule_GetPointer.restype = ctypes.c_void_p
+_PyCapsule_GetPointer.argtypes = [ctypes.py_object, ctypes.c_char_p]
+_PyCapsule_SetName = ctypes.pythonapi.PyCapsule_SetName
+_PyCapsule_SetName.restype = ctypes.c_int
+_PyCapsule_SetName.argtypes = [ctypes.py_object, ctypes.c_char_p]
+
+
+def _ptr(a):
+    """(address, y3_mem) of a numpy array or a torch tensor."""
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data, MEM_HOST
+    if hasattr(a, "data_ptr"):                                  # torch.Tensor
+        assert a.is_contiguous()
+        return a.data_ptr(), (MEM_DEVICE if a.is_cuda else MEM_HOST)
+    raise TypeError(type(a))
+
+
+def _capsule(t):
+    if isinstance(t, np.ndarray):
+        return np.ascontiguousarray(t, dtype=np.float32).__dlpack__()
+    import torch
+    from torch.utils.dlpack import to_dlpack
+    return to_dlpack(t.detach().to(torch.float32).contiguous())
+
+
+class Engine:
+    """One library handle.  img_size=None creates a post-processing-only handle."""
+
+    def __init__(self, img_size=None, number_classes=1, anchors=None, max_batch=1, device=0, max_candidates=0):
+        self.lib = _lib.load()
+        cfg = Y3Config()
+        cfg.struct_size = ctypes.sizeof(Y3Config)
+        anchors = list(anchors) if anchors is not None else list(DEFAULT_ANCHORS)
+        if img_size is not None:
+            cfg.img_h, cfg.img_w, cfg.img_c = int(img_size[0]), int(img_size[1]), int(img_size[2])
+        cfg.num_classes = int(number_classes)
+        cfg.num_anchors = len(anchors)
+        for i, (w, h) in enumerate(anchors):
+            cfg.anchors[i][0], cfg.anchors[i][1] = float(w), float(h)
+        cfg.max_batch = int(max_batch)
+        cfg.device = int(device)
+        cfg.max_candidates = int(max_candidates)
+        self.img_size = None if img_size is None else tuple(int(v) for v in img_size)
+        self.number_classes, self.anchors, self.max_batch, self.device = int(number_classes), anchors, int(max_batch), int(device)
+        h = ctypes.c_void_p()
+        check(self.lib.y3_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.y3_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights (DLPack)
+    def load_weights(self, weights):
+        """weights: {keras_variable_name: fp32 array (numpy or torch, host or CUDA)} in Keras layouts."""
+        names = list(weights.keys())
+        caps = [_capsule(weights[k]) for k in names]
+        n = len(names)
+        c_names = (ctypes.c_char_p * n)(*[k.encode() for k in names])
+        c_ptrs = (ctypes.c_void_p * n)(*[_PyCapsule_GetPointer(c, b"dltensor") for c in caps])
+        check(self.lib.y3_load_weights(self.h, n, c_names, c_ptrs), self.h)
+        for c in caps:                                          # consumed: the library ran the deleters
+            _PyCapsule_SetName(c, _USED)
+
+    # ------------------------------------------------------------------ network
+    @property
+    def boxes_per_image(self):
+        return int(self.lib.y3_boxes_per_image(self.h))
+
+    def forward_heads(self, batch):
+        """NCHW fp32 [B,C,H,W] -> three NCHW fp32 heads (model.py:462 get_keras_feature_map_model)."""
+        batch = np.ascontiguousarray(batch, dtype=np.float32) if isinstance(batch, np.ndarray) else batch
+        B = batch.shape[0]
+        H, W, _ = self.img_size
+        dc = len(self.anchors) * (5 + self.number_classes)
+        outs = [np.empty((B, dc, H // s, W // s), np.float32) for s in (32, 16, 8)]
+        p, mem = _ptr(batch)
+        check(self.lib.y3_forward_heads(self.h, p, mem, B, outs[0].ctypes.data, outs[1].ctypes.data,
+                                        outs[2].ctypes.data, MEM_HOST), self.h)
+        return outs
+
+    def forward_boxes(self, batch):
+        """yolo_model(batch, training=False): [B,C,H,W] -> [B,N,5+NC] fp32."""
+        batch = np.ascontiguousarray(batch, dtype=np.float32) if isinstance(batch, np.ndarray) else batch
+        B = batch.shape[0]
+        out = np.empty((B, self.boxes_per_image, 5 + self.number_classes), np.float32)
+        p, mem = _ptr(batch)
+        check(self.lib.y3_forward_boxes(self.h, p, mem, B, out.ctypes.data, MEM_HOST), self.h)
+        return out
+
+    def __call__(self, batch, training=False):
+        return self.forward_boxes(np.asarray(batch) if not hasattr(batch, "data_ptr") else batch)
+
+    def detect(self, batch, min_box_size=32, iou_threshold=0.3, score_threshold=0.1, cap=None):
+        """forward -> filter_small_boxes -> per_class_nms on the device.  -> boxes, scores, labels, img_index."""
+        batch = np.ascontiguousarray(batch, dtype=np.float32) if isinstance(batch, np.ndarray) else batch
+        B = batch.shape[0]
+        cap = int(cap) if cap else 1 << 16
+        p, mem = _ptr(batch)
+        while True:
+            ob = np.empty((cap, 4), np.float32)
+            os_ = np.empty(cap, np.float32)
+            ol = np.empty(cap, np.int32)
+            oi = np.empty(cap, np.int32)
+            n = ctypes.c_int64()
+            st = self.lib.y3_detect(self.h, p, mem, B, float(min_box_size), float(iou_threshold), float(score_threshold),
+                                    ob.ctypes.data, os_.ctypes.data, ol.ctypes.data, oi.ctypes.data, cap, ctypes.byref(n))
+            if st == _lib.ERR_NOSPACE and n.value > cap:
+                cap = int(n.value)
+                continue
+            check(st, self.h)
+            k = n.value
+            return ob[:k], os_[:k], ol[:k], oi[:k]
+
+    # ------------------------------------------------------------------ tiled
+    def infer_tiled(self, img, tile_size, min_box_size=32, edge_range=96, iou_threshold=0.3, score_threshold=0.1,
+                    tile_first=0, tile_count=-1, cap=None, out_device=None):
+        """inference_tiled.inference_image_tiled for tiles [tile_first, tile_first+tile_count).
+        img: HWC numpy (host) or torch CUDA tensor.  Returns float64 [n,6] (numpy, or a torch CUDA
+        tensor when out_device is a torch device - used for the NCCL all-gather)."""
+        H, W, C = (int(v) for v in img.shape)
+        dt = _DTYPES[np.dtype(img.dtype)] if isinstance(img, np.ndarray) else _torch_dtype(img)
+        p, mem = _ptr(img)
+        cap = int(cap) if cap else 1 << 16
+        while True:
+            if out_device is None:
+                out = np.empty((cap, 6), np.float64)
+                op, om = out.ctypes.data, MEM_HOST
+            else:
+                import torch
+                out = torch.empty((cap, 6), dtype=torch.float64, device=out_device)
+                op, om = out.data_ptr(), MEM_DEVICE
+            n = ctypes.c_int64()
+            st = self.lib.y3_infer_tiled(self.h, p, dt, mem, H, W, C, int(tile_size[0]), int(tile_size[1]), int(edge_range),
+                                         int(tile_first), int(tile_count), float(min_box_size), float(iou_threshold),
+                                         float(score_threshold), op, om, cap, ctypes.byref(n))
+            if st == _lib.ERR_NOSPACE and n.value > cap:
+                cap = int(n.value)
+                continue
+            check(st, self.h)
+            return out[:n.value]
+
+    def tiles_normalized(self, img, tile_size, edge_range=96, first=0, count=None):
+        H, W, C = (int(v) for v in img.shape)
+        total = tile_count(H, W, tile_size, edge_range)
+        count = total - first if count is None else count
+        out = np.empty((count, C, int(tile_size[0]), int(tile_size[1])), np.float32)
+        p, mem = _ptr(img)
+        check(self.lib.y3_tiles_normalized(self.h, p, _DTYPES[np.dtype(img.dtype)], mem, H, W, C, int(tile_size[0]),
+                                           int(tile_size[1]), int(edge_range), first, count, out.ctypes.data, MEM_HOST), self.h)
+        return out
+
+    def stitch_tiles(self, dets, img_hw, tile_size, min_box_size=32, edge_range=96, iou_threshold=0.3,
+                     score_threshold=0.1, first=0):
+        dets = np.ascontiguousarray(dets, dtype=np.float32)
+        T, N, E = dets.shape
+        cap = 1 << 16
+        while True:
+            out = np.empty((cap, 6), np.float64)
+            n = ctypes.c_int64()
+            st = self.lib.y3_stitch_tiles(self.h, dets.ctypes.data, MEM_HOST, N, E - 5, int(img_hw[0]), int(img_hw[1]),
+                                          int(tile_size[0]), int(tile_size[1]), int(edge_range), first, T, float(min_box_size),
+                                          float(iou_threshold), float(score_threshold), out.ctypes.data, MEM_HOST, cap, ctypes.byref(n))
+            if st == _lib.ERR_NOSPACE and n.value > cap:
+                cap = int(n.value)
+                continue
+            check(st, self.h)
+            return out[:n.value]
+
+    # ------------------------------------------------------------------ post-processing
+    def compute_iou(self, box, boxes):
+        box = np.ascontiguousarray(box, dtype=np.float32)
+        boxes = np.ascontiguousarray(boxes, dtype=np.float32)
+        out = np.empty(boxes.shape[0], np.float32)
+        check(self.lib.y3_compute_iou(self.h, box.ctypes.data, boxes.ctypes.data, boxes.shape[0], out.ctypes.data), self.h)
+        return out
+
+    def filter_small(self, rows, min_size):
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        n, L = rows.shape
+        out = np.empty((max(n, 1), L), np.float32)
+        k = ctypes.c_int64()
+        check(self.lib.y3_filter_small(self.h, rows.ctypes.data, n, L, float(min_size), out.ctypes.data, None, n,
+                                       ctypes.byref(k)), self.h)
+        return out[:k.value]
+
+    def single_class_nms(self, boxes, scores, iou_threshold):
+        boxes = np.ascontiguousarray(boxes, dtype=np.float32)
+        scores = np.ascontiguousarray(scores, dtype=np.float32)
+        m = boxes.shape[0]
+        keep = np.empty(max(m, 1), np.int32)
+        k = ctypes.c_int64()
+        check(self.lib.y3_single_class_nms(self.h, boxes.ctypes.data, scores.ctypes.data, m, float(iou_threshold),
+                                           keep.ctypes.data, ctypes.byref(k)), self.h)
+        return keep[:k.value]
+
+    def per_class_nms(self, boxes, objectness, class_probs, iou_threshold=0.3, score_threshold=0.1, with_src=False):
+        boxes = np.ascontiguousarray(boxes, dtype=np.float32)
+        obj = np.ascontiguousarray(objectness, dtype=np.float32).reshape(-1)
+        cls = np.ascontiguousarray(class_probs, dtype=np.float32)
+        n, nc = cls.shape
+        cap = max(min(n * nc, 1 << 20), 1)
+        while True:
+            ob = np.empty((cap, 4), np.float32)
+            os_ = np.empty(cap, np.float32)
+            ol = np.empty(cap, np.int32)
+            osrc = np.empty(cap, np.int32)
+            k = ctypes.c_int64()
+            st = self.lib.y3_per_class_nms(self.h, boxes.ctypes.data, obj.ctypes.data, cls.ctypes.data, n, nc,
+                                           float(iou_threshold), float(score_threshold), ob.ctypes.data, os_.ctypes.data,
+                                           ol.ctypes.data, osrc.ctypes.data, cap, ctypes.byref(k))
+            if st == _lib.ERR_NOSPACE and k.value > cap:
+                cap = int(k.value)
+                continue
+            check(st, self.h)
+            kk = k.value
+            if kk == 0:
+                return (None, None, None, None) if with_src else (None, None, None)
+            res = (ob[:kk], os_[:kk], ol[:kk])
+            return res + (osrc[:kk],) if with_src else res
+
+    # ------------------------------------------------------------------ measurement
+    def timings(self):
+        t = Y3Timings()
+        check(self.lib.y3_get_timings(self.h, ctypes.byref(t)), self.h)
+        return {f: getattr(t, f) for f, _ in Y3Timings._fields_}
+
+    def debug_layer_output(self, layer, batch):
+        """Test hook: NCHW fp32 output of one layer of the last forward (needs Y3_DEBUG_NO_REUSE at create)."""
+        H, W, _ = self.img_size
+        cap = batch * 32 * H * W
+        out = np.empty(cap, np.float32)
+        dims = (ctypes.c_int32 * 3)()
+        check(self.lib.y3_debug_layer_output(self.h, layer.encode(), batch, out.ctypes.data, cap, dims), self.h)
+        c, h, w = dims[0], dims[1], dims[2]
+        return out[:batch * c * h * w].reshape(batch, c, h, w).copy()
+
+    def bench_forward(self, batch, iters):
+        ms = ctypes.c_float()
+        check(self.lib.y3_bench_forward(self.h, int(batch), int(iters), ctypes.byref(ms)), self.h)
+        return ms.value
+
+
+def _torch_dtype(t):
+    import torch
+    return {torch.uint8: _lib.U8, torch.int32: _lib.I32, torch.float32: _lib.F32,
+            getattr(torch, "uint16", None): _lib.U16, torch.int16: _lib.U16}[t.dtype]
+
+
+def tile_count(img_h, img_w, tile_size, edge_range):
+    n = _lib.load().y3_tile_plan(int(img_h), int(img_w), int(tile_size[0]), int(tile_size[1]), int(edge_range), None, None, 0)
+    if n < 0:
+        raise _lib.Y3Error(int(n), "bad tile geometry")
+    return int(n)
+
+
+def tile_plan(img_h, img_w, tile_size, edge_range):
+    n = tile_count(img_h, img_w, tile_size, edge_range)
+    xs = np.empty(n, np.int32)
+    ys = np.empty(n, np.int32)
+    _lib.load().y3_tile_plan(int(img_h), int(img_w), int(tile_size[0]), int(tile_size[1]), int(edge_range),
+                             xs.ctypes.data, ys.ctypes.data, n)
+    return xs, ys
+
+
+_post = {}
+
+
+def post_engine(device=0):
+    """Process-wide post-processing handle (bbox_utils facade)."""
+    if device not in _post:
+        _post[device] = Engine(img_size=None, device=device)
+    return _post[device]

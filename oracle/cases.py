@@ -104,3 +104,13 @@ class FakeDetector:
         out = np.concatenate([(cx - w / 2)[:, None], (cy - h / 2)[:, None], (cx + w / 2)[:, None],
                               (cy + h / 2)[:, None], obj[:, None], self.cls], 1).astype(F32)
         return out[None]
+
+
+# (h, w, c, dtype, tile, edge) - tile slicing fixtures of tests/golden/tiling.npz
+TILE_CASES = dict(u16=(700, 900, 1, np.uint16, (512, 512), 96), u8rgb=(520, 1100, 3, np.uint8, (256, 320), 64),
+                  small=(300, 280, 1, np.uint16, (512, 512), 96), wide=(400, 1500, 1, np.uint16, (512, 512), 96))
+# (h, w, c, dtype, tile, edge, n_boxes, nc, min_box) - tests/golden/tiled_pipeline.npz
+PIPE_CASES = dict(e96=(1200, 1500, 1, np.uint16, (512, 512), 96, 900, 2, 32),
+                  e64=(1000, 1300, 1, np.uint16, (512, 512), 64, 700, 1, 32),
+                  rgb=(700, 640, 3, np.uint8, (256, 256), 32, 400, 3, 24),
+                  one=(300, 280, 1, np.uint16, (512, 512), 96, 300, 1, 32))

@@ -175,6 +175,7 @@ class OracleNet:
         # optional: emulate bf16 storage of every activation (used to size tolerances)
         self.round = round_activations
         self._it = None
+        self.trace = None          # set to {} to record every layer output by Keras name
 
     # -- layers ------------------------------------------------------------
     def _q(self, x):
@@ -199,14 +200,21 @@ class OracleNet:
         assert L["kind"] == kind, (L, kind)
         return L
 
+    def _rec(self, L, y):
+        if self.trace is not None:
+            self.trace[L["name"]] = y
+        return y
+
     def _cl(self, x):
-        return self._q(self._conv_layer(x, self._next("conv")))
+        L = self._next("conv")
+        return self._rec(L, self._q(self._conv_layer(x, L)))
 
     def _block(self, x, reps):
         y = x
         for _ in range(reps):
             y = self._cl(y)
-            y = self._q(x + self._conv_layer(y, self._next("conv")))     # Q5: adds the BLOCK input
+            L = self._next("conv")
+            y = self._rec(L, self._q(x + self._conv_layer(y, L)))       # Q5: adds the BLOCK input
         return y
 
     def _yolo(self, x):
@@ -222,7 +230,7 @@ class OracleNet:
     def _up(self, x):
         L = self._next("convt")
         w = self.w[L["name"] + "/kernel"].permute(3, 2, 0, 1)            # [Cin, Cout, kh, kw]
-        return self._q(F.conv_transpose2d(x, w, self.w[L["name"] + "/bias"], stride=2))
+        return self._rec(L, self._q(F.conv_transpose2d(x, w, self.w[L["name"] + "/bias"], stride=2)))
 
     # -- graph -------------------------------------------------------------
     @torch.no_grad()

@@ -54,8 +54,7 @@ def test_multiclass_80(golden):
     assert (sha(b), sha(s), sha(l)) == (str(g["mc80_sha_boxes"]), str(g["mc80_sha_scores"]), str(g["mc80_sha_labels"]))
 
 
-TILE_CASES = dict(u16=(700, 900, 1, np.uint16, (512, 512), 96), u8rgb=(520, 1100, 3, np.uint8, (256, 320), 64),
-                  small=(300, 280, 1, np.uint16, (512, 512), 96), wide=(400, 1500, 1, np.uint16, (512, 512), 96))
+TILE_CASES = cases.TILE_CASES
 
 
 @pytest.mark.parametrize("tag", list(TILE_CASES))
@@ -78,10 +77,7 @@ def test_zscore_flat_branch(golden):
     assert np.array_equal(tl.zscore(flat)[:2, :2, 0], g["flat_z"])
 
 
-PIPE_CASES = dict(e96=(1200, 1500, 1, np.uint16, (512, 512), 96, 900, 2, 32),
-                  e64=(1000, 1300, 1, np.uint16, (512, 512), 64, 700, 1, 32),
-                  rgb=(700, 640, 3, np.uint8, (256, 256), 32, 400, 3, 24),
-                  one=(300, 280, 1, np.uint16, (512, 512), 96, 300, 1, 32))
+PIPE_CASES = cases.PIPE_CASES
 
 
 @pytest.mark.parametrize("tag", list(PIPE_CASES))
