@@ -146,6 +146,13 @@ y3_status y3_per_class_nms(y3_handle h, const float* boxes /*[n,4]*/, const floa
 int64_t y3_tile_plan(int64_t img_h, int64_t img_w, int32_t tile_h, int32_t tile_w, int32_t edge_range,
                      int32_t* xs, int32_t* ys, int64_t cap);
 
+/* replaces: inference_tiled.convert_image_to_tiles pixels (inference_tiled.py:29-100): the raw tiles
+ * [first, first+count) in the SOURCE dtype, HWC each: out [count, tile_h, tile_w, C] (host|device). */
+y3_status y3_tiles_raw(y3_handle h, const void* img, y3_dtype dtype, y3_mem img_mem,
+                       int64_t img_h, int64_t img_w, int32_t img_c,
+                       int32_t tile_h, int32_t tile_w, int32_t edge_range,
+                       int64_t first, int64_t count, void* out, y3_mem out_mem);
+
 /* replaces: convert_image_to_tiles + astype(float32) + imagereader.zscore_normalize + HWC->NCHW
  * (inference_tiled.py:29-100, 202-212; imagereader.py:34-46) for tiles [first, first+count):
  * out [count, C, tile_h, tile_w] fp32 (host|device).  img is HWC (host|device). */
@@ -189,6 +196,12 @@ y3_status y3_get_timings(y3_handle h, y3_timings* out);
 /* Benchmark hook: run the conv stack only (no decode) `iters` times on the resident batch and
  * return the mean device ms per forward.  Used by bench.py for the roofline line. */
 y3_status y3_bench_forward(y3_handle h, int32_t batch, int32_t iters, float* ms_per_iter);
+
+/* Measurement hook: time every layer of the plan separately (CUDA events, `iters` repetitions each,
+ * on whatever the activation buffers currently hold) and write a CSV report
+ * "name,kind,k,stride,cin,cout,out_h,out_w,patch_h,patch_w,bn,bk,tiles,ms,tflops,min_gbytes_per_s"
+ * into buf (NUL-terminated, truncated to cap). */
+y3_status y3_profile_layers(y3_handle h, int32_t batch, int32_t iters, char* buf, int64_t cap);
 
 /* Test hook (not part of the reference surface): the output of one layer of the LAST forward as
  * NCHW fp32 [batch, C, H, W]; layer is a Keras layer name ("conv2d_7", "conv2d_transpose").

@@ -445,7 +445,28 @@ y3_status y3_tiles_normalized(y3_handle h, const void* img, y3_dtype dt, y3_mem 
         const TileGeo* d_geo = upload_geo(h, T, geo);
         const size_t bytes = (size_t)count * C * th * tw * 4;
         float* dst = out_mem == Y3_MEM_DEVICE ? out : (T->tiles.reserve(bytes), T->tiles.as<float>());
-        launch_tile_norm(h, d_img, dt, row_lo, (int)W, C, d_geo + first, (int)count, th, tw, dst, nullptr);
+        T->sums.reserve((size_t)count * 16);
+        launch_tile_norm(h, d_img, dt, row_lo, (int)W, C, d_geo + first, (int)count, th, tw, dst, nullptr, T->sums.as<double>());
+        if (out_mem != Y3_MEM_DEVICE) from_device(h, out, out_mem, dst, bytes);
+        Y3_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    Y3_API_END(h)
+}
+
+y3_status y3_tiles_raw(y3_handle h, const void* img, y3_dtype dt, y3_mem img_mem, int64_t H, int64_t W, int32_t C,
+                       int32_t th, int32_t tw, int32_t edge, int64_t first, int64_t count, void* out, y3_mem out_mem) {
+    Y3_API_BEGIN(h)
+    Y3_CHECK(img && out && H > 0 && W > 0 && C > 0, Y3_ERR_INVALID, "bad arguments");
+    Tiler* T = tiler_of(h);
+    std::vector<TileGeo> geo = plan_tiles(H, W, th, tw, edge, nullptr, nullptr);
+    Y3_CHECK(first >= 0 && count >= 0 && first + count <= (int64_t)geo.size(), Y3_ERR_INVALID, "tile range outside the plan");
+    if (count > 0) {
+        long long row_lo = 0;
+        const void* d_img = upload_band(h, T, img, dt, img_mem, W, C, geo, first, count, &row_lo);
+        const TileGeo* d_geo = upload_geo(h, T, geo);
+        const size_t bytes = (size_t)count * C * th * tw * dtype_size(dt);
+        void* dst = out_mem == Y3_MEM_DEVICE ? out : (T->tiles.reserve(bytes), T->tiles.p);
+        launch_tile_raw(h, d_img, (int)dtype_size(dt), row_lo, (int)W, C, d_geo + first, (int)count, th, tw, dst);
         if (out_mem != Y3_MEM_DEVICE) from_device(h, out, out_mem, dst, bytes);
         Y3_CUDA(cudaStreamSynchronize(h->stream));
     }
@@ -507,10 +528,11 @@ y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dt, y3_mem img_m
         StitchArgs S{H, W, th, tw, edge};
         const int B = net->maxB;
         T->tiles.reserve((size_t)B * C * th * tw * 4);
+        T->sums.reserve((size_t)B * 16);
         for (int64_t t0 = 0; t0 < tile_count; t0 += B) {
             const int nb = (int)std::min<int64_t>(B, tile_count - t0);
             const TileGeo* g = d_geo + tile_first + t0;
-            { Phase p(h, &Tm.ms_prep); launch_tile_norm(h, d_img, dt, row_lo, (int)W, C, g, nb, th, tw, T->tiles.as<float>(), nullptr); p.stop(); }
+            { Phase p(h, &Tm.ms_prep); launch_tile_norm(h, d_img, dt, row_lo, (int)W, C, g, nb, th, tw, T->tiles.as<float>(), nullptr, T->sums.as<double>()); p.stop(); }
             { Phase p(h, &Tm.ms_conv); net->forward(T->tiles.as<float>(), nb); p.stop(); }
             { Phase p(h, &Tm.ms_decode); net->decode(nb); p.stop(); }
             NmsResult R;
@@ -546,6 +568,17 @@ y3_status y3_bench_forward(y3_handle h, int32_t batch, int32_t iters, float* ms_
     for (int i = 0; i < iters; ++i) net->forward(h->stage_in.as<float>(), batch);
     p.stop();
     *ms_per_iter = acc / iters;
+    Y3_API_END(h)
+}
+
+y3_status y3_profile_layers(y3_handle h, int32_t batch, int32_t iters, char* buf, int64_t cap) {
+    Y3_API_BEGIN(h)
+    Net* net = net_of(h);
+    Y3_CHECK(buf && cap > 0 && iters >= 1 && batch >= 1 && batch <= net->maxB, Y3_ERR_INVALID, "bad arguments");
+    const std::string rep = net->profile(batch, iters);
+    const size_t n = std::min<size_t>(rep.size(), (size_t)cap - 1);
+    memcpy(buf, rep.data(), n);
+    buf[n] = 0;
     Y3_API_END(h)
 }
 

@@ -121,6 +121,22 @@ __device__ __forceinline__ float iou_exact(const float4 a, const float area_a, c
     const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
     return __fdiv_rn(inter, uni);
 }
+// single_class_nms survivor test `iou <= thr` (bbox_utils.py:233) negated, bit-exact, without the
+// division for the common non-overlapping pair: inter == 0 gives iou = 0/union, i.e. +-0 (survives
+// iff 0 <= thr) unless union is 0 or NaN (0/0 -> NaN -> suppressed).
+__device__ __forceinline__ bool suppresses_exact(const float4 a, const float area_a, const float4 b, const float area_b,
+                                                 const float thr) {
+    const float xl = np_max(a.x, b.x);
+    const float yt = np_max(a.y, b.y);
+    const float xr = np_min(a.z, b.z);
+    const float yb = np_min(a.w, b.w);
+    const float dh = np_max(__fsub_rn(yb, yt), 0.0f);
+    const float dw = np_max(__fsub_rn(xr, xl), 0.0f);
+    const float inter = __fmul_rn(dh, dw);
+    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    if (inter == 0.0f) return !((uni != 0.0f) && (uni == uni) && (0.0f <= thr));
+    return !(__fdiv_rn(inter, uni) <= thr);
+}
 __device__ __forceinline__ float box_area_exact(const float4 b) {
     return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
 }

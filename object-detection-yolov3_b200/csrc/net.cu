@@ -455,6 +455,56 @@ void Net::decode(int b) {
     launch_decode(ctx, D, boxes.as<float>());
 }
 
+std::string Net::profile(int b, int iters) {
+    Y3_CHECK(loaded, Y3_ERR_STATE, "weights not loaded");
+    cudaStream_t st = ctx->stream;
+    std::string out = "name,kind,k,stride,cin,cout,out_h,out_w,patch_h,patch_w,bn,bk,tiles,ms,tflops,min_gbytes_per_s\n";
+    cudaEvent_t e0, e1;
+    Y3_CUDA(cudaEventCreate(&e0)); Y3_CUDA(cudaEventCreate(&e1));
+    stage.reserve((size_t)b * C * H * W * 4);
+    for (Op& op : ops) {
+        if (op.kind != Op::STEM) set_batch(op, b);
+        auto run = [&]() {
+            if (op.kind == Op::STEM)
+                launch_stem(ctx, stage.as<float>(), reinterpret_cast<__nv_bfloat16*>(tensors[op.out.t].ptr), op.w.as<float>(),
+                            op.bias.as<float>(), op.scale.as<float>(), op.shift.as<float>(), b, H, W, C);
+            else
+                for (const ConvLaunch& L : op.launches) launch_conv(ctx, L);
+        };
+        run();
+        Y3_CUDA(cudaEventRecord(e0, st));
+        for (int i = 0; i < iters; ++i) run();
+        Y3_CUDA(cudaEventRecord(e1, st));
+        Y3_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        Y3_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        ms /= iters;
+        int oh, ow;
+        if (op.kind == Op::DET) { oh = gh[op.head]; ow = gw[op.head]; }
+        else { oh = tensors[op.out.t].h; ow = tensors[op.out.t].w; }
+        const int taps = op.kind == Op::CONVT ? 4 : op.k * op.k;
+        const double mpix = (double)b * (op.kind == Op::CONVT ? oh * ow / 4 : oh * ow);
+        const double flops = 2.0 * mpix * op.cout * taps * op.cin;
+        const double in_px = op.kind == Op::STEM ? (double)b * H * W : (double)b * tensors[op.in.t].h * tensors[op.in.t].w;
+        double bytes = in_px * op.cin * (op.kind == Op::STEM ? 4 : 2) + (double)b * oh * ow * op.cout * (op.kind == Op::DET ? 4 : 2)
+                       + (double)op.cout * taps * op.cin * 2;
+        if (op.res_t >= 0) bytes += (double)b * oh * ow * op.cout * 2;
+        const char* kind = op.kind == Op::STEM ? "stem" : op.kind == Op::CONV ? "conv" : op.kind == Op::DET ? "det" : "convt";
+        int bh = 0, bw = 0, bn = 0, bk = 0, tiles = 0;
+        if (!op.launches.empty()) {
+            const ConvLaunch& L = op.launches[0];
+            bh = L.args.BH; bw = L.args.BW; bn = L.bn; bk = L.bk; tiles = L.args.total_tiles * (int)op.launches.size();
+        }
+        char line[512];
+        snprintf(line, sizeof(line), "%s,%s,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.1f,%.1f\n", op.name.c_str(), kind, op.k, op.stride,
+                 op.cin, op.cout, oh, ow, bh, bw, bn, bk, tiles, ms, flops / (ms * 1e-3) / 1e12, bytes / (ms * 1e-3) / 1e9);
+        out += line;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cur_batch = b;
+    return out;
+}
+
 Net::~Net() {
     for (void* p : owned) cudaFree(p);
 }

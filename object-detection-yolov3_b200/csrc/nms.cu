@@ -31,7 +31,7 @@ namespace y3 {
 static constexpr int NMS_T = 512;             // boxes per chunk
 static constexpr int NMS_W = NMS_T / 64;      // mask words per row
 static constexpr int NMS_THREADS = 256;
-static constexpr int64_t BIG_SEGMENT = 8192;  // segments above this use resolve/apply launches
+static constexpr int64_t BIG_SEGMENT = 32768; // segments above this use resolve/apply launches (whole GPU per segment)
 
 // ------------------------------------------------------------------------------------------
 // orderable score bits: ascending unsigned order == ascending float order
@@ -170,8 +170,7 @@ __device__ __forceinline__ void chunk_resolve(ChunkSmem& S, const float4* __rest
         const int jn = min(64, ct - j0);
         for (int b = 0; b < jn; ++b) {
             const int j = j0 + b;
-            const float iou = iou_exact(bi, ai, S.box[j], S.area[j]);
-            if (j > i && !(iou <= thr)) bits |= (1ull << b);
+            if (j > i && suppresses_exact(bi, ai, S.box[j], S.area[j], thr)) bits |= (1ull << b);
         }
         S.mask[i * NMS_W + w] = bits;
     }
@@ -223,8 +222,7 @@ k_nms_segments(const float4* __restrict__ sbox, const float* __restrict__ sarea,
                 const float aj = sarea[s0 + j];
                 for (int t = 0; t < nk; ++t) {
                     const int k = S.klist[t];
-                    const float iou = iou_exact(S.box[k], S.area[k], bj, aj);
-                    if (!(iou <= thr)) { supp[s0 + j] = 1; break; }
+                    if (suppresses_exact(S.box[k], S.area[k], bj, aj, thr)) { supp[s0 + j] = 1; break; }
                 }
             }
             __syncthreads();
@@ -266,8 +264,7 @@ k_nms_apply(const float4* __restrict__ sbox, const float* __restrict__ sarea, ui
         const float4 bj = sbox[j];
         const float aj = sarea[j];
         for (int t = 0; t < nk; ++t) {
-            const float iou = iou_exact(s_box[t], s_area[t], bj, aj);
-            if (!(iou <= thr)) { supp[j] = 1; break; }
+            if (suppresses_exact(s_box[t], s_area[t], bj, aj, thr)) { supp[j] = 1; break; }
         }
     }
 }

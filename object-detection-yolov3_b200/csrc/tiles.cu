@@ -6,8 +6,8 @@
 //   image and np.pad(mode='reflect') back to the tile size; r = 0 on an axis whose tile covers the
 //   image.  The RECORDED origin is the clamped one (SURVEY Q12 - border tiles are shifted by +r; kept).
 //   Each tile is z-scored with its own mean / population std over all channels (Q14); std <= 1 means
-//   "subtract the mean only".  One CTA per tile: two-pass fp64 statistics (mean, then sum of squared
-//   deviations), then a third pass writes (x - mean) / std as NCHW fp32.  The image stays resident in
+//   "subtract the mean only".  16 CTAs per tile: shifted fp64 sums (exact for integer images), then a
+//   second kernel writes (x - mean) / std as NCHW fp32.  The image stays resident in
 //   HBM in its source dtype; the reflect is index arithmetic, no padded copy is ever made.
 // Back-end   (inference_tiled.py:235-301)
 //   ghost-band ownership by box centre, origin add (fp32), np.round (half-to-even) -> int32,
@@ -75,44 +75,98 @@ __device__ __forceinline__ double block_sum(double v, double* s_red) {
     return s_red[32];
 }
 
-__global__ void __launch_bounds__(1024)
-k_tile_norm(const void* __restrict__ img, int dtype, long long row_lo, int W, int C, const TileGeo* __restrict__ geo,
-            int th, int tw, float* __restrict__ out, float* __restrict__ stats) {
-    __shared__ double s_red[33];
-    const TileGeo g = geo[blockIdx.x];
-    const int ny = g.y1 - g.y0, nx = g.x1 - g.x0;
-    const int n_el = th * tw * C;
+static constexpr int TILE_SPLIT = 16;      // CTAs per tile (one CTA per tile left 116 of 148 SMs idle)
+
+__device__ __forceinline__ float tile_fetch(const void* __restrict__ img, int dtype, long long row_lo, int W, int C,
+                                            const TileGeo& g, int th, int tw, int e) {
     // element e -> (c, ty, tx) with tx fastest (coalesced NCHW writes)
-    auto fetch = [&](int e) -> float {
-        const int tx = e % tw;
-        const int r = e / tw;
-        const int ty = r % th;
-        const int c = r / th;
-        const int sy = g.y0 + reflect_idx(ty - g.pre_y, ny);
-        const int sx = g.x0 + reflect_idx(tx - g.pre_x, nx);
-        return load_any(img, dtype, ((long long)(sy - row_lo) * W + sx) * C + c);
-    };
-    double acc = 0.0;
-    for (int e = threadIdx.x; e < n_el; e += blockDim.x) acc += (double)fetch(e);
-    const double mean = block_sum(acc, s_red) / (double)n_el;
-    acc = 0.0;
-    for (int e = threadIdx.x; e < n_el; e += blockDim.x) { const double d = (double)fetch(e) - mean; acc += d * d; }
-    const double var = block_sum(acc, s_red) / (double)n_el;
-    const float mu = (float)mean;
-    const float sd = (float)sqrt(var);
-    float* o = out + (long long)blockIdx.x * n_el;
-    if (sd <= 1.0f) {
-        for (int e = threadIdx.x; e < n_el; e += blockDim.x) o[e] = __fsub_rn(fetch(e), mu);
-    } else {
-        for (int e = threadIdx.x; e < n_el; e += blockDim.x) o[e] = __fdiv_rn(__fsub_rn(fetch(e), mu), sd);
+    const int tx = e % tw;
+    const int r = e / tw;
+    const int ty = r % th;
+    const int c = r / th;
+    const int sy = g.y0 + reflect_idx(ty - g.pre_y, g.y1 - g.y0);
+    const int sx = g.x0 + reflect_idx(tx - g.pre_x, g.x1 - g.x0);
+    return load_any(img, dtype, ((long long)(sy - row_lo) * W + sx) * C + c);
+}
+
+// pass 1: per-tile sum(x - s) and sum((x - s)^2) in fp64, s = the tile's first element (a shift that
+// removes the cancellation of the one-pass variance; for integer images every partial sum is an exact
+// integer < 2^53, so the result does not depend on the order of the atomics).
+__global__ void __launch_bounds__(512)
+k_tile_stats(const void* __restrict__ img, int dtype, long long row_lo, int W, int C, const TileGeo* __restrict__ geo,
+             int th, int tw, double* __restrict__ sums /*[count][2]*/) {
+    __shared__ double s_red[33];
+    const TileGeo g = geo[blockIdx.y];
+    const int n_el = th * tw * C;
+    const double shift = (double)tile_fetch(img, dtype, row_lo, W, C, g, th, tw, 0);
+    double a1 = 0.0, a2 = 0.0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += gridDim.x * blockDim.x) {
+        const double d = (double)tile_fetch(img, dtype, row_lo, W, C, g, th, tw, e) - shift;
+        a1 += d;
+        a2 += d * d;
     }
-    if (stats && threadIdx.x == 0) { stats[2 * blockIdx.x] = mu; stats[2 * blockIdx.x + 1] = sd; }
+    a1 = block_sum(a1, s_red);
+    a2 = block_sum(a2, s_red);
+    if (threadIdx.x == 0) {
+        atomicAdd(&sums[2 * blockIdx.y], a1);
+        atomicAdd(&sums[2 * blockIdx.y + 1], a2);
+    }
+}
+
+// pass 2: (x - mean) / std, or x - mean when std <= 1 (imagereader.py:38-44), NCHW fp32
+__global__ void __launch_bounds__(512)
+k_tile_write(const void* __restrict__ img, int dtype, long long row_lo, int W, int C, const TileGeo* __restrict__ geo,
+             int th, int tw, const double* __restrict__ sums, float* __restrict__ out, float* __restrict__ stats) {
+    const TileGeo g = geo[blockIdx.y];
+    const int n_el = th * tw * C;
+    const double shift = (double)tile_fetch(img, dtype, row_lo, W, C, g, th, tw, 0);
+    const double m1 = sums[2 * blockIdx.y] / (double)n_el;
+    double var = sums[2 * blockIdx.y + 1] / (double)n_el - m1 * m1;
+    if (var < 0.0) var = 0.0;
+    const float mu = (float)(shift + m1);
+    const float sd = (float)sqrt(var);
+    float* o = out + (long long)blockIdx.y * n_el;
+    const bool center_only = sd <= 1.0f;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += gridDim.x * blockDim.x) {
+        const float d = __fsub_rn(tile_fetch(img, dtype, row_lo, W, C, g, th, tw, e), mu);
+        o[e] = center_only ? d : __fdiv_rn(d, sd);
+    }
+    if (stats && blockIdx.x == 0 && threadIdx.x == 0) { stats[2 * blockIdx.y] = mu; stats[2 * blockIdx.y + 1] = sd; }
 }
 
 void launch_tile_norm(y3_context* ctx, const void* img_dev, int dtype, long long row_lo, int W, int C,
-                      const TileGeo* geo_dev, int count, int th, int tw, float* out, float* stats) {
+                      const TileGeo* geo_dev, int count, int th, int tw, float* out, float* stats, double* sums_scratch) {
     if (count <= 0) return;
-    k_tile_norm<<<count, 1024, 0, ctx->stream>>>(img_dev, dtype, row_lo, W, C, geo_dev, th, tw, out, stats);
+    Y3_CUDA(cudaMemsetAsync(sums_scratch, 0, (size_t)count * 16, ctx->stream));
+    dim3 grid(TILE_SPLIT, count);
+    k_tile_stats<<<grid, 512, 0, ctx->stream>>>(img_dev, dtype, row_lo, W, C, geo_dev, th, tw, sums_scratch);
+    Y3_LAUNCHED(ctx);
+    k_tile_write<<<grid, 512, 0, ctx->stream>>>(img_dev, dtype, row_lo, W, C, geo_dev, th, tw, sums_scratch, out, stats);
+    Y3_LAUNCHED(ctx);
+}
+
+// raw (un-normalised) tiles in the source dtype, HWC - the return value of convert_image_to_tiles
+__global__ void __launch_bounds__(256)
+k_tile_raw(const unsigned char* __restrict__ img, int esize, long long row_lo, int W, int C, const TileGeo* __restrict__ geo,
+           int th, int tw, unsigned char* __restrict__ out) {
+    const TileGeo g = geo[blockIdx.y];
+    const int ny = g.y1 - g.y0, nx = g.x1 - g.x0;
+    const int n_px = th * tw;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_px; p += gridDim.x * blockDim.x) {
+        const int ty = p / tw, tx = p - ty * tw;
+        const int sy = g.y0 + reflect_idx(ty - g.pre_y, ny);
+        const int sx = g.x0 + reflect_idx(tx - g.pre_x, nx);
+        const unsigned char* src = img + (((long long)(sy - row_lo) * W + sx) * C) * esize;
+        unsigned char* dst = out + (((long long)blockIdx.y * n_px + p) * C) * esize;
+        for (int b = 0; b < C * esize; ++b) dst[b] = src[b];
+    }
+}
+void launch_tile_raw(y3_context* ctx, const void* img_dev, int esize, long long row_lo, int W, int C,
+                     const TileGeo* geo_dev, int count, int th, int tw, void* out) {
+    if (count <= 0) return;
+    dim3 grid((th * tw + 255) / 256 > 64 ? 64 : (th * tw + 255) / 256, count);
+    k_tile_raw<<<grid, 256, 0, ctx->stream>>>(static_cast<const unsigned char*>(img_dev), esize, row_lo, W, C, geo_dev, th, tw,
+                                              static_cast<unsigned char*>(out));
     Y3_LAUNCHED(ctx);
 }
 

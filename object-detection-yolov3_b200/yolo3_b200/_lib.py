@@ -50,6 +50,8 @@ PROTOTYPES = {
     "y3_tile_plan": (c_int64, [c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int64]),
     "y3_tiles_normalized": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int64, c_int32, c_int32,
                                       c_int32, c_int32, c_int64, c_int64, c_void_p, c_int32]),
+    "y3_tiles_raw": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int64, c_int32, c_int32,
+                               c_int32, c_int32, c_int64, c_int64, c_void_p, c_int32]),
     "y3_stitch_tiles": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int64, c_int64, c_int32, c_int32,
                                   c_int32, c_int64, c_int64, c_float, c_float, c_float, c_void_p, c_int32, c_int64,
                                   POINTER(c_int64)]),
@@ -58,6 +60,7 @@ PROTOTYPES = {
                                  POINTER(c_int64)]),
     "y3_get_timings": (c_int32, [c_void_p, POINTER(Y3Timings)]),
     "y3_bench_forward": (c_int32, [c_void_p, c_int32, c_int32, POINTER(c_float)]),
+    "y3_profile_layers": (c_int32, [c_void_p, c_int32, c_int32, c_char_p, c_int64]),
     "y3_debug_layer_output": (c_int32, [c_void_p, c_char_p, c_int32, c_void_p, c_int64, POINTER(c_int32)]),
 }
 

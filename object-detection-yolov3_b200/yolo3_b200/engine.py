@@ -144,7 +144,7 @@ class Engine:
         H, W, C = (int(v) for v in img.shape)
         dt = _DTYPES[np.dtype(img.dtype)] if isinstance(img, np.ndarray) else _torch_dtype(img)
         p, mem = _ptr(img)
-        cap = int(cap) if cap else 1 << 16
+        cap = int(cap) if cap else getattr(self, "_tiled_cap", 1 << 16)
         while True:
             if out_device is None:
                 out = np.empty((cap, 6), np.float64)
@@ -158,7 +158,7 @@ class Engine:
                                          int(tile_first), int(tile_count), float(min_box_size), float(iou_threshold),
                                          float(score_threshold), op, om, cap, ctypes.byref(n))
             if st == _lib.ERR_NOSPACE and n.value > cap:
-                cap = int(n.value)
+                cap = self._tiled_cap = 2 * int(n.value)       # sticky: later calls do not recompute
                 continue
             check(st, self.h)
             return out[:n.value]
@@ -171,6 +171,16 @@ class Engine:
         p, mem = _ptr(img)
         check(self.lib.y3_tiles_normalized(self.h, p, _DTYPES[np.dtype(img.dtype)], mem, H, W, C, int(tile_size[0]),
                                            int(tile_size[1]), int(edge_range), first, count, out.ctypes.data, MEM_HOST), self.h)
+        return out
+
+    def tiles_raw(self, img, tile_size, edge_range=96, first=0, count=None):
+        H, W, C = (int(v) for v in img.shape)
+        total = tile_count(H, W, tile_size, edge_range)
+        count = total - first if count is None else count
+        out = np.empty((count, int(tile_size[0]), int(tile_size[1]), C), img.dtype)
+        p, mem = _ptr(img)
+        check(self.lib.y3_tiles_raw(self.h, p, _DTYPES[np.dtype(img.dtype)], mem, H, W, C, int(tile_size[0]),
+                                    int(tile_size[1]), int(edge_range), first, count, out.ctypes.data, MEM_HOST), self.h)
         return out
 
     def stitch_tiles(self, dets, img_hw, tile_size, min_box_size=32, edge_range=96, iou_threshold=0.3,
@@ -248,6 +258,12 @@ class Engine:
         check(self.lib.y3_get_timings(self.h, ctypes.byref(t)), self.h)
         return {f: getattr(t, f) for f, _ in Y3Timings._fields_}
 
+    def profile_layers(self, batch, iters=5):
+        """Measurement hook: per-layer CSV (name, shapes, tile config, ms, TFLOP/s, minimum GB/s)."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        check(self.lib.y3_profile_layers(self.h, int(batch), int(iters), buf, len(buf)), self.h)
+        return buf.value.decode()
+
     def debug_layer_output(self, layer, batch):
         """Test hook: NCHW fp32 output of one layer of the last forward (needs Y3_DEBUG_NO_REUSE at create)."""
         H, W, _ = self.img_size
@@ -294,3 +310,37 @@ def post_engine(device=0):
     if device not in _post:
         _post[device] = Engine(img_size=None, device=device)
     return _post[device]
+
+
+def shard_range(n_tiles, rank, world):
+    """contiguous (row-band) tile range of one rank"""
+    per = (n_tiles + world - 1) // world
+    first = min(rank * per, n_tiles)
+    return first, min(per, n_tiles - first)
+
+
+def infer_tiled_distributed(eng, img, tile_size, min_box_size=32, edge_range=96, iou_threshold=0.3,
+                            score_threshold=0.1, group=None):
+    """inference_image_tiled with the tile grid sharded across the ranks of a torch.distributed
+    (NCCL) group: every rank runs its row band of tiles on its own GPU (slice, normalise, conv stack,
+    decode, NMS, ownership filter - no data-path collective), then the surviving boxes are
+    all-gathered over NVLink and concatenated in rank (= tile) order.  -> torch float64 [n,6] (CUDA)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n_tiles = tile_count(img.shape[0], img.shape[1], tile_size, edge_range)
+    first, count = shard_range(n_tiles, rank, world)
+    dev = torch.device("cuda", eng.device)
+    local = eng.infer_tiled(img, tile_size, min_box_size, edge_range, iou_threshold, score_threshold,
+                            tile_first=first, tile_count=count, out_device=dev)
+    n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    padded = torch.zeros((cap, 6), dtype=torch.float64, device=dev)
+    padded[:local.shape[0]] = local
+    gathered = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(gathered, padded, group=group)
+    return torch.cat([g[:c] for g, c in zip(gathered, counts)], 0)
