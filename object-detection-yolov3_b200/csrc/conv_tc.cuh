@@ -27,7 +27,8 @@ struct ConvArgs {
 struct ConvLaunch {
     CUtensorMap map_a, map_b, map_out, map_res;
     ConvArgs args;
-    int bn, bk;              // template selection
+    int bn, bk;              // template selection (two_cta: bn = N of the pair UMMA, 128 or 256)
+    int two_cta;             // use the cta_group::2 kernel (conv_tc2.cu)
     int grid;
 };
 
@@ -36,5 +37,6 @@ void encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64
                       const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box, int swizzle_bytes);
 
 void launch_conv(y3_context* ctx, const ConvLaunch& L);
+void launch_conv2(y3_context* ctx, const ConvLaunch& L);
 
 }  // namespace y3

@@ -222,6 +222,9 @@ void Net::make_launches(Op& op) {
     int bn = op.cout_pad >= 128 ? 128 : op.cout_pad;
     if (bk == 32) Y3_CHECK(bn == 64, Y3_ERR_UNSUPPORTED, "layer %s: Cin 32 needs Cout 64", op.name.c_str());
     Y3_CHECK(bn == 128 || bn == 64 || bn == 32, Y3_ERR_UNSUPPORTED, "layer %s: Cout %d unsupported", op.name.c_str(), op.cout_pad);
+    // 2-CTA pairs (cta_group::2): M = 256 per pair, N = 128 or 256 - halves the L2->smem bytes per FLOP
+    const bool two = (bk == 64) && (op.cout_pad >= 128) && (op.cout_pad % 128 == 0) && !getenv("Y3_DISABLE_2CTA");
+    if (two) bn = (op.cout_pad % 256 == 0) ? 256 : 128;
     const int oc = bn < 64 ? bn : 64;
     const int n_sub = op.kind == Op::CONVT ? 4 : 1;
     const int taps = op.kind == Op::CONVT ? 1 : op.k * op.k;
@@ -231,7 +234,7 @@ void Net::make_launches(Op& op) {
         ConvLaunch L;
         memset(&L, 0, sizeof(L));
         ConvArgs& A = L.args;
-        L.bn = bn; L.bk = bk;
+        L.bn = bn; L.bk = bk; L.two_cta = two ? 1 : 0;
         A.taps = taps; A.kwn = op.k == 3 ? 3 : 1;
         A.cin = cin; A.kchunks = cin / bk;
         A.stride = op.kind == Op::CONVT ? 1 : op.stride;
@@ -276,7 +279,7 @@ void Net::make_launches(Op& op) {
             const __nv_bfloat16* wbase = op.w.as<__nv_bfloat16>() + (size_t)sub * op.cout * cin;
             uint64_t dims[2] = {ktot, (uint64_t)op.cout_pad};
             uint64_t str[1] = {ktot * 2};
-            uint32_t box[2] = {(uint32_t)bk, (uint32_t)bn};
+            uint32_t box[2] = {(uint32_t)bk, (uint32_t)(two ? bn / 2 : bn)};
             encode_tmap_bf16(&L.map_b, wbase, 2, dims, str, box, bk * 2);
         }
         // ---- output
@@ -338,7 +341,12 @@ void Net::set_batch(Op& op, int b) {
             A.tiles_per_img = A.tiles_x * A.tiles_y; A.n_img = b;
         }
         A.total_tiles = A.tiles_per_img * A.n_img * A.n_tiles_n;
-        L.grid = std::min(A.total_tiles, ctx->sm_count);
+        if (L.two_cta) {
+            const int pair_tiles = ((A.tiles_per_img * A.n_img + 1) / 2) * A.n_tiles_n;
+            L.grid = 2 * std::min(pair_tiles, ctx->sm_count / 2);
+        } else {
+            L.grid = std::min(A.total_tiles, ctx->sm_count);
+        }
     }
 }
 
