@@ -319,6 +319,25 @@ def shard_range(n_tiles, rank, world):
     return first, min(per, n_tiles - first)
 
 
+def gather_rows(local, group=None):
+    """All-gather a variable number of [n, 6] rows from every rank and concatenate them in rank order
+    (counts first, then padded records) - the only exchange step of the tiled path.  Works on whatever
+    device `local` lives on (NCCL for CUDA tensors, gloo for CPU tensors in the host-logic tests)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    padded = torch.zeros((cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    gathered = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(gathered, padded, group=group)
+    return torch.cat([g[:c] for g, c in zip(gathered, counts)], 0)
+
+
 def infer_tiled_distributed(eng, img, tile_size, min_box_size=32, edge_range=96, iou_threshold=0.3,
                             score_threshold=0.1, group=None):
     """inference_image_tiled with the tile grid sharded across the ranks of a torch.distributed
@@ -334,13 +353,4 @@ def infer_tiled_distributed(eng, img, tile_size, min_box_size=32, edge_range=96,
     dev = torch.device("cuda", eng.device)
     local = eng.infer_tiled(img, tile_size, min_box_size, edge_range, iou_threshold, score_threshold,
                             tile_first=first, tile_count=count, out_device=dev)
-    n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
-    counts = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(counts, n_local, group=group)
-    counts = [int(c.item()) for c in counts]
-    cap = max(max(counts), 1)
-    padded = torch.zeros((cap, 6), dtype=torch.float64, device=dev)
-    padded[:local.shape[0]] = local
-    gathered = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(gathered, padded, group=group)
-    return torch.cat([g[:c] for g, c in zip(gathered, counts)], 0)
+    return gather_rows(local, group)

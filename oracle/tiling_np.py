@@ -137,3 +137,28 @@ def tiled_inference(model_fn, img, tile_size, min_roi_size, edge_range=96,
     b, s, l = finish_boxes(np.concatenate(acc_b), np.concatenate(acc_s), np.concatenate(acc_l), (H, W))
     return np.concatenate((b.astype(np.float64), s.astype(np.float64)[:, None],
                            l.astype(np.float64)[:, None]), axis=1)
+
+
+def tiled_inference_single_tile(model_fn, img, tile_size, min_roi_size, edge_range, tile_index,
+                                iou_threshold=0.3, score_threshold=0.1, nms_fn=pp.greedy_nms):
+    """The rows of tiled_inference() that come from ONE tile (tile-major output => the full result is
+    the concatenation over tiles).  Used to check the rank-sharded path on the CPU."""
+    H, W = img.shape[0], img.shape[1]
+    tiles, xs, ys = cut_tiles(img, tile_size, edge_range)
+    t, ox, oy = tiles[tile_index], xs[tile_index], ys[tile_index]
+    x = zscore(t.astype(F32)).transpose(2, 0, 1)[None]
+    det = np.asarray(model_fn(np.ascontiguousarray(x)))[0]
+    det = pp.drop_small(det, min_roi_size)
+    b, s, l = pp.class_wise_nms(det[:, 0:4], det[:, 4:5], det[:, 5:], iou_threshold, score_threshold, nms_fn=nms_fn)
+    if b is None:
+        return np.zeros((0, 6), np.float64)
+    bad = ghost_band_mask(b, ox, oy, (H, W), tile_size, edge_range)
+    b, s, l = b[~bad].copy(), s[~bad], l[~bad]
+    if b.shape[0] == 0:
+        return np.zeros((0, 6), np.float64)
+    b[:, 0] += ox
+    b[:, 2] += ox
+    b[:, 1] += oy
+    b[:, 3] += oy
+    b, s, l = finish_boxes(b, s, l, (H, W))
+    return np.concatenate((b.astype(np.float64), s.astype(np.float64)[:, None], l.astype(np.float64)[:, None]), axis=1)
