@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(128)
 k_stem(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, const float* __restrict__ w /*[9*CIN][32]*/,
        const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
        int B, int H, int W) {
+    // each thread produces TWO horizontally adjacent pixels x 32 channels: every weight float4 read from
+    // shared memory feeds 8 FMAs, and the 3x4 input patch is shared by both pixels
     __shared__ float4 s_w[9 * CIN * 8];
     __shared__ float4 s_p[3 * 8];
     for (int i = threadIdx.x; i < 9 * CIN * 8; i += blockDim.x) s_w[i] = reinterpret_cast<const float4*>(w)[i];
@@ -27,63 +29,75 @@ k_stem(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, const floa
         s_p[16 + threadIdx.x] = reinterpret_cast<const float4*>(shift)[threadIdx.x];
     }
     __syncthreads();
-    const long long npix = (long long)B * H * W;
-    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
-         pix += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(pix % W);
-        const long long t = pix / W;
+    const int W2 = W >> 1;                                   // W is a multiple of 32
+    const long long npair = (long long)B * H * W2;
+    for (long long pp = (long long)blockIdx.x * blockDim.x + threadIdx.x; pp < npair;
+         pp += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(pp % W2) * 2;
+        const long long t = pp / W2;
         const int y = (int)(t % H);
         const int b = (int)(t / H);
-        float acc[32];
+        float acc0[32], acc1[32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+        for (int c = 0; c < 32; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-            const int yy = y + kh - 1;
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float* plane = in + ((long long)b * CIN + ci) * H * W;
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const int xx = x + kw - 1;
-                const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+            for (int kh = 0; kh < 3; ++kh) {
+                const int yy = y + kh - 1;
+                const bool yok = (yy >= 0) && (yy < H);
+                float v[4];
 #pragma unroll
-                for (int ci = 0; ci < CIN; ++ci) {
-                    const float v = ok ? __ldg(in + (((long long)b * CIN + ci) * H + yy) * W + xx) : 0.f;
+                for (int j = 0; j < 4; ++j) {
+                    const int xx = x + j - 1;
+                    v[j] = (yok && xx >= 0 && xx < W) ? __ldg(plane + (long long)yy * W + xx) : 0.f;
+                }
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
                     const float4* wr = s_w + ((kh * 3 + kw) * CIN + ci) * 8;
+                    const float a0 = v[kw], a1 = v[kw + 1];
 #pragma unroll
                     for (int c4 = 0; c4 < 8; ++c4) {
                         const float4 ww = wr[c4];
-                        acc[4 * c4 + 0] = fmaf(v, ww.x, acc[4 * c4 + 0]);
-                        acc[4 * c4 + 1] = fmaf(v, ww.y, acc[4 * c4 + 1]);
-                        acc[4 * c4 + 2] = fmaf(v, ww.z, acc[4 * c4 + 2]);
-                        acc[4 * c4 + 3] = fmaf(v, ww.w, acc[4 * c4 + 3]);
+                        acc0[4 * c4 + 0] = fmaf(a0, ww.x, acc0[4 * c4 + 0]); acc1[4 * c4 + 0] = fmaf(a1, ww.x, acc1[4 * c4 + 0]);
+                        acc0[4 * c4 + 1] = fmaf(a0, ww.y, acc0[4 * c4 + 1]); acc1[4 * c4 + 1] = fmaf(a1, ww.y, acc1[4 * c4 + 1]);
+                        acc0[4 * c4 + 2] = fmaf(a0, ww.z, acc0[4 * c4 + 2]); acc1[4 * c4 + 2] = fmaf(a1, ww.z, acc1[4 * c4 + 2]);
+                        acc0[4 * c4 + 3] = fmaf(a0, ww.w, acc0[4 * c4 + 3]); acc1[4 * c4 + 3] = fmaf(a1, ww.w, acc1[4 * c4 + 3]);
                     }
                 }
             }
         }
-        uint32_t o[16];
+        const long long pix = ((long long)b * H + y) * W + x;
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-            const float4 bb = s_p[c4], ss = s_p[8 + c4], tt = s_p[16 + c4];
-            float z0 = acc[4 * c4 + 0] + bb.x, z1 = acc[4 * c4 + 1] + bb.y;
-            float z2 = acc[4 * c4 + 2] + bb.z, z3 = acc[4 * c4 + 3] + bb.w;
-            z0 = (z0 > 0.f ? z0 : 0.2f * z0) * ss.x + tt.x;
-            z1 = (z1 > 0.f ? z1 : 0.2f * z1) * ss.y + tt.y;
-            z2 = (z2 > 0.f ? z2 : 0.2f * z2) * ss.z + tt.z;
-            z3 = (z3 > 0.f ? z3 : 0.2f * z3) * ss.w + tt.w;
-            __nv_bfloat162 a = __floats2bfloat162_rn(z0, z1), c = __floats2bfloat162_rn(z2, z3);
-            o[2 * c4] = *reinterpret_cast<uint32_t*>(&a);
-            o[2 * c4 + 1] = *reinterpret_cast<uint32_t*>(&c);
+        for (int half = 0; half < 2; ++half) {
+            const float* acc = half ? acc1 : acc0;
+            uint32_t o[16];
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 bb = s_p[c4], ss = s_p[8 + c4], tt = s_p[16 + c4];
+                float z0 = acc[4 * c4 + 0] + bb.x, z1 = acc[4 * c4 + 1] + bb.y;
+                float z2 = acc[4 * c4 + 2] + bb.z, z3 = acc[4 * c4 + 3] + bb.w;
+                z0 = (z0 > 0.f ? z0 : 0.2f * z0) * ss.x + tt.x;
+                z1 = (z1 > 0.f ? z1 : 0.2f * z1) * ss.y + tt.y;
+                z2 = (z2 > 0.f ? z2 : 0.2f * z2) * ss.z + tt.z;
+                z3 = (z3 > 0.f ? z3 : 0.2f * z3) * ss.w + tt.w;
+                __nv_bfloat162 a = __floats2bfloat162_rn(z0, z1), c = __floats2bfloat162_rn(z2, z3);
+                o[2 * c4] = *reinterpret_cast<uint32_t*>(&a);
+                o[2 * c4 + 1] = *reinterpret_cast<uint32_t*>(&c);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(out + (pix + half) * 32);
+            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+            dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
         }
-        uint4* dst = reinterpret_cast<uint4*>(out + pix * 32);
-        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-        dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
-        dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
     }
 }
 
 void launch_stem(y3_context* ctx, const float* in, __nv_bfloat16* out, const float* w, const float* bias,
                  const float* scale, const float* shift, int B, int H, int W, int cin) {
-    const long long npix = (long long)B * H * W;
+    const long long npix = (long long)B * H * W / 2;        // two pixels per thread
     const int blocks = (int)std::min<long long>((npix + 127) / 128, (long long)ctx->sm_count * 64);
     if (cin == 1) k_stem<1><<<blocks, 128, 0, ctx->stream>>>(in, out, w, bias, scale, shift, B, H, W);
     else if (cin == 3) k_stem<3><<<blocks, 128, 0, ctx->stream>>>(in, out, w, bias, scale, shift, B, H, W);

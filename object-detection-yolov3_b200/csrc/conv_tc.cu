@@ -25,6 +25,7 @@
 //     NHWC buffer; the transposed conv is 4 such GEMMs scattered by the output map's strides.
 #include "conv_tc.cuh"
 #include "ptx.cuh"
+#include <algorithm>
 
 namespace y3 {
 using namespace ptx;
@@ -42,7 +43,9 @@ struct ConvCfg {
     static constexpr int NCHUNK = BN / OC;
     static constexpr int CHUNK_BYTES = TILE_M * OCB;
     static constexpr int STG_BYTES = TILE_M * BN * 2;
-    static constexpr int STAGES = (BN == 128 && BK == 64) ? 4 : (BK == 64 ? 6 : 8);
+    // small configs run 2 CTAs per SM (their tiles are latency-chained, not bandwidth-bound per CTA)
+    static constexpr int CTAS_PER_SM = (BN == 128) ? 1 : 2;
+    static constexpr int STAGES = (BN == 128 && BK == 64) ? 4 : (BK == 64 ? 3 : 4);
     static constexpr int BAR_BYTES = (2 * STAGES + 8) * 8 + 16;
     static constexpr int SMEM = 1024 + STAGES * STAGE_BYTES + 2 * STG_BYTES + BAR_BYTES;
     static constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
@@ -50,7 +53,7 @@ struct ConvCfg {
     static constexpr uint32_t SBO = 8 * BK * 2;
     static_assert(STAGE_BYTES % 1024 == 0 && A_BYTES % 1024 == 0, "operand tiles must stay 1024-B aligned");
     static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns: power of two <= 512");
-    static_assert(SMEM <= 232448, "exceeds 227 KB of shared memory");
+    static_assert(SMEM * CTAS_PER_SM <= 232448 - 1024 * CTAS_PER_SM, "exceeds 227 KB of shared memory");
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -61,7 +64,7 @@ __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u <
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
 template <int BN, int BK>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(CONV_THREADS, ConvCfg<BN, BK>::CTAS_PER_SM)
 k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
           const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
           const ConvArgs P) {
@@ -269,12 +272,18 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     for (int ch = 0; ch < C::NCHUNK; ++ch)
                         tma_store_4d(&map_out, stg + ch * C::CHUNK_BYTES, n0 + ch * C::OC, x0, y0, img);
                     tma_store_commit();
-                    tma_store_wait_read();                 // staging buffer reusable
-                    if (P.has_res) mbar_arrive(&stg_empty[p]);
+                    if (P.has_res) {
+                        tma_store_wait_read();             // residual prefetch may overwrite this buffer
+                        mbar_arrive(&stg_empty[p]);
+                    } else {
+                        tma_store_wait_read_keep1();       // double-buffered staging: only the buffer written
+                    }                                      // two tiles ago must be drained; this store overlaps
+
                 }
             }
         }
     }
+    if (warp == 2 && lane == 0) tma_store_wait_read();     // smem must outlive the last TMA store's reads
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
@@ -332,7 +341,8 @@ static void launch_t(y3_context* ctx, const ConvLaunch& L) {
         Y3_CUDA(cudaFuncSetAttribute(k_conv_tc<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr[ctx->device & 63] = true;
     }
-    k_conv_tc<BN, BK><<<L.grid, CONV_THREADS, C::SMEM, ctx->stream>>>(L.map_a, L.map_b, L.map_out, L.map_res, L.args);
+    const int grid = std::min(L.args.total_tiles, ctx->sm_count * C::CTAS_PER_SM);
+    k_conv_tc<BN, BK><<<grid, CONV_THREADS, C::SMEM, ctx->stream>>>(L.map_a, L.map_b, L.map_out, L.map_res, L.args);
     Y3_LAUNCHED(ctx);
 }
 

@@ -16,6 +16,7 @@
 //     the non-leader's epilogue releases the accumulator with a remote mbarrier arrive.
 #include "conv_tc.cuh"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace y3 {
 using namespace ptx;
@@ -23,7 +24,7 @@ using namespace ptx;
 static constexpr int CONV2_THREADS = 64 + 256;
 static constexpr int TILE_M2 = 128;     // rows per CTA (the pair computes 256)
 
-template <int BN2>
+template <int BN2, int NSTG_>
 struct Conv2Cfg {
     static constexpr int BK = 64;
     static constexpr int A_BYTES = TILE_M2 * BK * 2;
@@ -32,8 +33,8 @@ struct Conv2Cfg {
     static constexpr int NCHUNK = BN2 / 64;
     static constexpr int CHUNK_BYTES = TILE_M2 * 128;
     static constexpr int STG_BYTES = TILE_M2 * BN2 * 2;
-    static constexpr int NSTG = (BN2 == 256) ? 1 : 2;             // staging buffers
-    static constexpr int STAGES = (BN2 == 256) ? 4 : 6;
+    static constexpr int NSTG = NSTG_;                            // staging buffers (1: serialised store/residual)
+    static constexpr int STAGES = (BN2 == 256) ? (NSTG_ == 1 ? 4 : 3) : 6;
     static constexpr int BAR_BYTES = (2 * STAGES + 8) * 8 + 16;
     static constexpr int SMEM = 1024 + STAGES * STAGE_BYTES + NSTG * STG_BYTES + BAR_BYTES;
     static constexpr uint32_t TMEM_COLS = 2 * BN2;
@@ -47,12 +48,12 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int BN2>
+template <int BN2, int NSTG_>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV2_THREADS, 1)
 k_conv_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
            const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, const ConvArgs P) {
 #if defined(__CUDA_ARCH_FEAT_SM100_ALL) || defined(__CUDA_ARCH_FEAT_SM101_ALL)
-    using C = Conv2Cfg<BN2>;
+    using C = Conv2Cfg<BN2, NSTG_>;
     constexpr int BK = C::BK;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -273,13 +274,18 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                         for (int ch = 0; ch < C::NCHUNK; ++ch)
                             tma_store_4d(&map_out, stg + ch * C::CHUNK_BYTES, n0 + ch * 64, x0, y0, img);
                     tma_store_commit();
-                    tma_store_wait_read();
-                    if (P.has_res) mbar_arrive(&stg_empty[sp]);
+                    if (P.has_res || C::NSTG == 1) {
+                        tma_store_wait_read();
+                        if (P.has_res) mbar_arrive(&stg_empty[sp]);
+                    } else {
+                        tma_store_wait_read_keep1();          // overlap this store with the next tile's epilogue
+                    }
                 }
                 if (C::NSTG == 1) named_bar_sync(2, 256);     // single staging buffer: wait until it was read
             }
         }
     }
+    if (warp == 2 && lane == 0) tma_store_wait_read();
     tc_fence_before();
     cluster_sync_all();
     if (warp == 2) tmem_dealloc2<C::TMEM_COLS>(tmem_base);
@@ -289,21 +295,23 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
 #endif
 }
 
-template <int BN2>
+template <int BN2, int NSTG_>
 static void launch2_t(y3_context* ctx, const ConvLaunch& L) {
-    using C = Conv2Cfg<BN2>;
+    using C = Conv2Cfg<BN2, NSTG_>;
     static bool attr[64] = {};
     if (!attr[ctx->device & 63]) {
-        Y3_CUDA(cudaFuncSetAttribute(k_conv_tc2<BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        Y3_CUDA(cudaFuncSetAttribute(k_conv_tc2<BN2, NSTG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr[ctx->device & 63] = true;
     }
-    k_conv_tc2<BN2><<<L.grid, CONV2_THREADS, C::SMEM, ctx->stream>>>(L.map_a, L.map_b, L.map_out, L.map_res, L.args);
+    k_conv_tc2<BN2, NSTG_><<<L.grid, CONV2_THREADS, C::SMEM, ctx->stream>>>(L.map_a, L.map_b, L.map_out, L.map_res, L.args);
     Y3_LAUNCHED(ctx);
 }
 
 void launch_conv2(y3_context* ctx, const ConvLaunch& L) {
-    if (L.bn == 256) launch2_t<256>(ctx, L);
-    else if (L.bn == 128) launch2_t<128>(ctx, L);
+    static const int stg256 = getenv("Y3_CONV2_STG") ? atoi(getenv("Y3_CONV2_STG")) : 2;
+    if (L.bn == 256 && stg256 == 1) launch2_t<256, 1>(ctx, L);
+    else if (L.bn == 256) launch2_t<256, 2>(ctx, L);
+    else if (L.bn == 128) launch2_t<128, 2>(ctx, L);
     else fail(Y3_ERR_UNSUPPORTED, "no 2-CTA conv kernel for BN2=%d", L.bn);
 }
 

@@ -71,9 +71,9 @@ void Net::add_det(View in, int idx) {
     Op op;
     op.kind = Op::DET;
     op.name = "feature_map_" + std::to_string(idx + 1);
-    op.cin = in.c; op.cout = det_c; op.cout_pad = HEAD_PITCH; op.k = 1; op.stride = 1;
+    op.cin = in.c; op.cout = det_c; op.cout_pad = head_pitch; op.k = 1; op.stride = 1;
     op.in = in; op.head = idx;
-    Y3_CHECK(det_c <= HEAD_PITCH, Y3_ERR_UNSUPPORTED, "A*(5+NC) = %d exceeds %d head channels", det_c, HEAD_PITCH);
+    Y3_CHECK(det_c <= HEAD_PITCH_MAX, Y3_ERR_UNSUPPORTED, "A*(5+NC) = %d exceeds %d head channels", det_c, HEAD_PITCH_MAX);
     ops.push_back(std::move(op));
 }
 
@@ -93,6 +93,7 @@ void Net::build() {
     Y3_CHECK(C >= 1 && C <= 4, Y3_ERR_UNSUPPORTED, "image channels %d not in 1..4", C);
     Y3_CHECK(na >= 1 && na <= Y3_MAX_ANCHORS && nc >= 1 && maxB >= 1, Y3_ERR_INVALID, "bad anchors/classes/batch");
     det_c = na * (5 + nc);
+    head_pitch = det_c <= 32 ? 32 : det_c <= 64 ? 64 : det_c <= 128 ? 128 : 256;
     for (int s = 0; s < 3; ++s) { gh[s] = H / (32 >> s); gw[s] = W / (32 >> s); }
     rows_per_image = 0;
     for (int s = 0; s < 3; ++s) { row_start[s] = (int)rows_per_image; rows_per_image += (int64_t)gh[s] * gw[s] * na; }
@@ -167,7 +168,7 @@ void Net::build() {
             if (tensors[t].last == (int)i && tensors[t].ptr) free_list.insert({tensors[t].bytes, tensors[t].ptr});
     }
     for (int s = 0; s < 3; ++s) {
-        const size_t bytes = (size_t)maxB * gh[s] * gw[s] * HEAD_PITCH * 4;
+        const size_t bytes = (size_t)maxB * gh[s] * gw[s] * head_pitch * 4;
         Y3_CUDA(cudaMalloc((void**)&head[s], bytes));
         owned.push_back(head[s]);
     }
@@ -224,7 +225,15 @@ void Net::make_launches(Op& op) {
     Y3_CHECK(bn == 128 || bn == 64 || bn == 32, Y3_ERR_UNSUPPORTED, "layer %s: Cout %d unsupported", op.name.c_str(), op.cout_pad);
     // 2-CTA pairs (cta_group::2): M = 256 per pair, N = 128 or 256 - halves the L2->smem bytes per FLOP
     const bool two = (bk == 64) && (op.cout_pad >= 128) && (op.cout_pad % 128 == 0) && !getenv("Y3_DISABLE_2CTA");
-    if (two) bn = (op.cout_pad % 256 == 0) ? 256 : 128;
+    if (two) {
+        bn = (op.cout_pad % 256 == 0) ? 256 : 128;
+        // few, short tiles (1x1 layers deep in the net): N = 128 pair tiles double the tile count, which
+        // balances the 74 CTA pairs better than it costs in A re-reads from L2
+        static const int small_opt = getenv("Y3_BN2_SMALL") ? atoi(getenv("Y3_BN2_SMALL")) : 0;
+        const long long m_rows = (long long)maxB * (op.kind == Op::CONVT ? ti.h * ti.w : (ti.h / op.stride) * (ti.w / op.stride));
+        const long long pair_tiles_256 = ((m_rows / 128 + 1) / 2) * (op.cout_pad / 256 > 0 ? op.cout_pad / 256 : 1);
+        if (small_opt && bn == 256 && op.k == 1 && pair_tiles_256 < 3LL * (ctx->sm_count / 2)) bn = 128;
+    }
     const int oc = bn < 64 ? bn : 64;
     const int n_sub = op.kind == Op::CONVT ? 4 : 1;
     const int taps = op.kind == Op::CONVT ? 1 : op.k * op.k;
@@ -285,7 +294,7 @@ void Net::make_launches(Op& op) {
         // ---- output
         if (op.kind == Op::DET) {
             A.out32 = head[op.head];
-            A.out32_pitch = HEAD_PITCH;
+            A.out32_pitch = head_pitch;
             L.map_out = L.map_a;   // unused
             L.map_res = L.map_a;
         } else {
@@ -459,7 +468,7 @@ void Net::decode(int b) {
         D.stride_w[s] = floorf((float)W / (float)gw[s]);
     }
     for (int a = 0; a < na; ++a) { D.anchor_w[a] = ctx->cfg.anchors[a][0]; D.anchor_h[a] = ctx->cfg.anchors[a][1]; }
-    D.na = na; D.nc = nc; D.pitch = HEAD_PITCH; D.n_total = (int)rows_per_image; D.batch = b;
+    D.na = na; D.nc = nc; D.pitch = head_pitch; D.n_total = (int)rows_per_image; D.batch = b;
     launch_decode(ctx, D, boxes.as<float>());
 }
 

@@ -6,7 +6,7 @@
 
 namespace y3 {
 
-static constexpr int HEAD_PITCH = 256;   // fp32 channels per pixel of a stored head (A*(5+NC) padded)
+static constexpr int HEAD_PITCH_MAX = 256;   // fp32 channels per pixel of a stored head: A*(5+NC) padded to 32/64/128/256
 
 struct TensorInfo {
     int h = 0, w = 0, c = 0;
@@ -47,7 +47,7 @@ struct Op {
 
 struct Net {
     y3_context* ctx;
-    int H = 0, W = 0, C = 0, nc = 0, na = 0, maxB = 0, det_c = 0;
+    int H = 0, W = 0, C = 0, nc = 0, na = 0, maxB = 0, det_c = 0, head_pitch = 256;
     int gh[3], gw[3], row_start[3];
     int64_t rows_per_image = 0;
     double conv_flops_per_image = 0;

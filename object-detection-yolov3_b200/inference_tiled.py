@@ -21,7 +21,7 @@ import model
 from bbox_utils import compute_iou, filter_small_boxes, per_class_nms, single_class_nms  # noqa: F401
 from yolo3_b200 import infer_tiled_distributed, post_engine, tile_plan
 
-BATCH_SIZE = 32          # tiles per forward batch (declared but unused in the reference)
+BATCH_SIZE = 64          # tiles per forward batch (declared but unused in the reference)
 EDGE_EFFECT_RANGE = 96
 
 
