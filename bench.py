@@ -54,14 +54,14 @@ def bench_weights(seed=0):
     return weights.random_init(1, NC, len(ANCHORS), seed=seed, randomize_bn=True)
 
 
-def calibrate_heads(eng, w, sample_tiles, target_std=1.0, obj_bias=-6.0):
+def calibrate_heads(eng, w, sample_tiles, target_std=1.0, obj_bias=-6.0, nc=NC, n_anchors=len(ANCHORS)):
     """Random-init heads are useless as a detection regime: the all-ones upsample inflates the three heads
     by 400x relative to each other and every output channel is a large constant plus a small spatial
     signal, so whole channels pass or fail the score threshold together.  Standardise every detection
     channel (measured on the GPU path itself over sample tiles) to logits ~ N(0, target_std) and shift
     the objectness channels by obj_bias -> a sparse, spatially varying set of candidates."""
     heads = eng.forward_heads(sample_tiles)
-    E = 5 + NC
+    E = 5 + nc
     upd = {}
     for i, h in enumerate(heads):
         k = "feature_map_%d" % (i + 1)
@@ -70,11 +70,11 @@ def calibrate_heads(eng, w, sample_tiles, target_std=1.0, obj_bias=-6.0):
         core = h[:, :, m:g - m, m:g - m]                    # borders would otherwise dominate the statistics
         mu = core.mean(axis=(0, 2, 3)).astype(np.float64)
         sd = np.maximum(core.std(axis=(0, 2, 3)).astype(np.float64), 1e-12)
-        tgt = np.full((len(ANCHORS), E), target_std)
+        tgt = np.full((n_anchors, E), target_std)
         tgt[:, 2:4] = 0.3                                   # box-size logits: boxes stay near their anchor size
         gain = tgt.reshape(-1) / sd
-        want = np.zeros(len(ANCHORS) * E)
-        want.reshape(len(ANCHORS), E)[:, 4] = obj_bias
+        want = np.zeros(n_anchors * E)
+        want.reshape(n_anchors, E)[:, 4] = obj_bias
         upd[k + "/kernel"] = (w[k + "/kernel"] * gain[None, None, None, :]).astype(np.float32)
         upd[k + "/bias"] = (want + (w[k + "/bias"] - mu) * gain).astype(np.float32)
     eng.load_weights(upd)
@@ -291,6 +291,35 @@ def main():
             line["aux_nms_k3"] = {"boxes": 200_000, "classes": 1, "iou_thr": 0.45, "kept": int(keep.size),
                                   "boxes_per_s_e2e_host_arrays": 200_000 / dt_nms,
                                   "boxes_per_s_device": 200_000 / (tn["ms_nms"] * 1e-3), "ms_nms_device": tn["ms_nms"]}
+            # auxiliary: BASELINE configs[1] (416x416x3, batch 64, NC=80) - conv stack TFLOP/s and the fused
+            # decode + threshold + compaction + NMS stage against HBM bandwidth on SURVEY 8(d)'s byte model
+            # B*N*(5+NC)*4 (heads read once) + K_cand*56 + k_kept*4
+            try:
+                from yolo3_b200 import weights as _wts
+                del eng
+                torch.cuda.empty_cache()
+                e2 = Engine((416, 416, 3), 80, ANCHORS, max_batch=64, device=local)
+                w2 = _wts.random_init(3, 80, 3, seed=0, randomize_bn=True)
+                e2.load_weights(w2)
+                x2 = np.random.default_rng(1).standard_normal((64, 3, 416, 416)).astype(np.float32)
+                calibrate_heads(e2, w2, x2[:4], obj_bias=-7.5, nc=80)
+                e2.detect(x2, MIN_BOX, IOU_THR, SCORE_THR)
+                e2.detect(x2, MIN_BOX, IOU_THR, SCORE_THR)
+                t2 = e2.timings()
+                nbytes = 64 * 10647 * 85 * 4 + t2["candidates"] * 56 + t2["kept"] * 4
+                hbm = float(peaks.get("hbm_gbs", 6650.0))
+                line["aux_k2_416_b64_nc80"] = {
+                    "conv_ms": t2["ms_conv"], "conv_tflops": 64 * 66.12988928e9 / (t2["ms_conv"] * 1e-3) / 1e12,
+                    "decode_nms_ms": t2["ms_nms"], "candidates": int(t2["candidates"]), "kept": int(t2["kept"]),
+                    "decode_nms_algorithmic_gbytes_per_s": nbytes / (t2["ms_nms"] * 1e-3) / 1e9,
+                    "decode_nms_frac_of_hbm": nbytes / (t2["ms_nms"] * 1e-3) / 1e9 / hbm,
+                    "decode_threshold_compact_kernel_ms": t2["ms_decode"],
+                    "decode_threshold_compact_kernel_gbytes_per_s": 64 * 10647 * 85 * 4 / (t2["ms_decode"] * 1e-3) / 1e9,
+                    "decode_threshold_compact_kernel_frac_of_hbm": 64 * 10647 * 85 * 4 / (t2["ms_decode"] * 1e-3) / 1e9 / hbm,
+                    "images_per_s_device": 64 / (t2["ms_total"] * 1e-3)}
+                del e2
+            except Exception as ex:                      # auxiliary only - never fail the headline line
+                line["aux_k2_416_b64_nc80"] = {"error": str(ex)[:200]}
             threads = os.cpu_count() or 1
             v, dt = cpu_baseline_run(img[:4096, :4096], edge, args.cpu_sample_tiles, threads)
             line["cpu_baseline"] = {"value": v, "unit": "Mpix/s", "cores": threads, "kind": "port",

@@ -185,7 +185,8 @@ y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dtype, y3_mem im
 
 /* Measurement hooks (not part of the reference surface): device time in ms of the stages of the
  * last y3_detect / y3_infer_tiled / NMS call, measured with CUDA events on the handle's stream,
- * and the number of kernels this library launched since the handle was created. */
+ * and the number of kernels this library launched since the handle was created.  ms_decode is the fused
+ * decode + threshold + small-box filter + compaction kernel alone (it is also contained in ms_nms). */
 typedef struct {
     float ms_total, ms_h2d, ms_prep, ms_conv, ms_decode, ms_nms, ms_stitch, ms_d2h;
     int64_t kernels_launched;

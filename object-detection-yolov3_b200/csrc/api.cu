@@ -120,6 +120,16 @@ CandSource dets_source(const float* dets_dev, int64_t n_per_img, int n_img, int 
     return s;
 }
 
+// fused: the candidates are thresholded straight from the raw heads of the last forward
+CandSource heads_source(const Net* net, int n_img, bool filter, float min_box, float score_thr) {
+    CandSource s;
+    s.from_heads = true;
+    s.dec = net->decode_args(n_img);
+    s.rows_per_image = net->rows_per_image; s.n_images = n_img; s.nc = net->nc;
+    s.filter_small = filter; s.min_size = min_box; s.score_thr = score_thr;
+    return s;
+}
+
 }  // namespace
 
 // ============================================================================================
@@ -244,12 +254,12 @@ y3_status y3_detect(y3_handle h, const float* in, y3_mem in_mem, int32_t batch, 
     const float* d_in;
     { Phase p(h, &T.ms_h2d); d_in = static_cast<const float*>(to_device(h, in, in_mem, in_bytes, h->stage_in)); p.stop(); }
     { Phase p(h, &T.ms_conv); net->forward(d_in, batch); p.stop(); }
-    { Phase p(h, &T.ms_decode); net->decode(batch); p.stop(); }
     NmsResult R;
-    {
+    {   // decode + score + threshold + small-box filter + compaction fused in one pass over the heads
         Phase p(h, &T.ms_nms);
-        R = post_of(h)->run(dets_source(net->boxes.as<float>(), net->rows_per_image, batch, net->nc, true, min_box, score_thr), iou_thr);
+        R = post_of(h)->run(heads_source(net, batch, true, min_box, score_thr), iou_thr);
         p.stop();
+        T.ms_decode = post_of(h)->last_cand_ms;      // the fused decode+threshold+compaction kernel alone
     }
     T.candidates = R.n_cand; T.kept = R.n_kept;
     *n_out = R.n_kept;
@@ -534,11 +544,10 @@ y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dt, y3_mem img_m
             const TileGeo* g = d_geo + tile_first + t0;
             { Phase p(h, &Tm.ms_prep); launch_tile_norm(h, d_img, dt, row_lo, (int)W, C, g, nb, th, tw, T->tiles.as<float>(), nullptr, T->sums.as<double>()); p.stop(); }
             { Phase p(h, &Tm.ms_conv); net->forward(T->tiles.as<float>(), nb); p.stop(); }
-            { Phase p(h, &Tm.ms_decode); net->decode(nb); p.stop(); }
             NmsResult R;
             { Phase p(h, &Tm.ms_nms);
-              R = P->run(dets_source(net->boxes.as<float>(), net->rows_per_image, nb, net->nc, true, min_box, score_thr), iou_thr);
-              p.stop(); }
+              R = P->run(heads_source(net, nb, true, min_box, score_thr), iou_thr);
+              p.stop(); Tm.ms_decode += P->last_cand_ms; }
             Tm.candidates += R.n_cand; Tm.kept += R.n_kept;
             { Phase p(h, &Tm.ms_stitch); T->stitch(P, R, g, S); p.stop(); }
         }

@@ -184,11 +184,7 @@ void slice_to_nchw(y3_context* ctx, const __nv_bfloat16* in, float* out, int B, 
 
 // ------------------------------------------------------------------------------------------ decode
 // One thread per output element of [B, N, 5+NC].  A head stored NHWC with channel a*(5+NC)+k is already
-// in output row order, so this is a pure element-wise map.  Arithmetic is fp32 in the
-// reference's operand order with no FMA contraction:
-//   cx = (sigmoid(tx) + j) * stride ; w = exp(tw) * anchor_w ; x0 = cx - w / 2 ; x1 = cx + w / 2
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
-
+// in output row order, so this is a pure element-wise map (helpers in aux_kernels.cuh).
 __global__ void __launch_bounds__(256)
 k_decode(DecodeArgs D, float* __restrict__ out) {
     const int E = 5 + D.nc;
@@ -199,30 +195,9 @@ k_decode(DecodeArgs D, float* __restrict__ out) {
         const long long r = i - (long long)b * per_img;
         const int row = (int)(r / E);
         const int k = (int)(r - (long long)row * E);
-        int s = 0;
-        if (row >= D.row_start[1]) s = 1;
-        if (row >= D.row_start[2]) s = 2;
-        const int lr = row - D.row_start[s];
-        const int cell = lr / D.na;
-        const int a = lr - cell * D.na;
-        const float* hp = D.head[s] + ((long long)b * D.gh[s] * D.gw[s] + cell) * D.pitch + a * E;
-        float v;
-        if (k >= 4) {
-            v = sigmoid_f(__ldg(hp + k));
-        } else {
-            const int axis = k & 1;                         // 0: x, 1: y
-            const float tc = __ldg(hp + axis);
-            const float ts = __ldg(hp + 2 + axis);
-            const int gi = cell / D.gw[s], gj = cell - gi * D.gw[s];
-            const float off = axis == 0 ? (float)gj : (float)gi;
-            // model.py:127,157 - the (h,w) stride pair multiplies the (x,y) pair as written
-            const float stride = axis == 0 ? D.stride_h[s] : D.stride_w[s];
-            const float c = __fmul_rn(__fadd_rn(sigmoid_f(tc), off), stride);
-            const float wh = __fmul_rn(expf(ts), axis == 0 ? D.anchor_w[a] : D.anchor_h[a]);
-            const float half = __fdiv_rn(wh, 2.0f);
-            v = (k < 2) ? __fsub_rn(c, half) : __fadd_rn(c, half);
-        }
-        out[i] = v;
+        int s, cell, a;
+        const float* hp = head_row(D, b, row, &s, &cell, &a);
+        out[i] = (k >= 4) ? sigmoid_f(__ldg(hp + k)) : decode_corner(D, hp, s, cell, a, k);
     }
 }
 void launch_decode(y3_context* ctx, const DecodeArgs& D, float* out) {

@@ -13,6 +13,39 @@ struct DecodeArgs {
     int na, nc, pitch, n_total, batch;
 };
 
+#ifdef __CUDACC__
+// reorg_layer + convert_feature_map_to_inference_detections (model.py:122-212), one output element.
+// fp32 in the reference's operand order, no FMA contraction:
+//   cx = (sigmoid(tx) + j) * stride ; w = exp(tw) * anchor_w ; x0 = cx - w / 2 ; x1 = cx + w / 2
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+// pointer to the (5+NC) logits of output row `row` of image b, plus its grid cell / anchor / scale
+__device__ __forceinline__ const float* head_row(const DecodeArgs& D, int b, int row, int* s_out, int* cell_out, int* a_out) {
+    int s = 0;
+    if (row >= D.row_start[1]) s = 1;
+    if (row >= D.row_start[2]) s = 2;
+    const int lr = row - D.row_start[s];
+    const int cell = lr / D.na;
+    const int a = lr - cell * D.na;
+    *s_out = s; *cell_out = cell; *a_out = a;
+    return D.head[s] + ((long long)b * D.gh[s] * D.gw[s] + cell) * D.pitch + a * (5 + D.nc);
+}
+// k in 0..3 : x0, y0, x1, y1
+__device__ __forceinline__ float decode_corner(const DecodeArgs& D, const float* hp, int s, int cell, int a, int k) {
+    const int axis = k & 1;                         // 0: x, 1: y
+    const float tc = __ldg(hp + axis);
+    const float ts = __ldg(hp + 2 + axis);
+    const int gi = cell / D.gw[s], gj = cell - gi * D.gw[s];
+    const float off = axis == 0 ? (float)gj : (float)gi;
+    // model.py:127,157 - the (h,w) stride pair multiplies the (x,y) pair as written
+    const float stride = axis == 0 ? D.stride_h[s] : D.stride_w[s];
+    const float c = __fmul_rn(__fadd_rn(sigmoid_f(tc), off), stride);
+    const float wh = __fmul_rn(expf(ts), axis == 0 ? D.anchor_w[a] : D.anchor_h[a]);
+    const float half = __fdiv_rn(wh, 2.0f);
+    return (k < 2) ? __fsub_rn(c, half) : __fadd_rn(c, half);
+}
+#endif
+
 void launch_stem(y3_context* ctx, const float* in, __nv_bfloat16* out, const float* w, const float* bias,
                  const float* scale, const float* shift, int B, int H, int W, int cin);
 void pack_conv_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, int taps, int cin, int cout, int cout_pad);

@@ -458,7 +458,7 @@ void Net::forward(const float* in_dev, int b) {
     cur_batch = b;
 }
 
-void Net::decode(int b) {
+DecodeArgs Net::decode_args(int b) const {
     DecodeArgs D;
     memset(&D, 0, sizeof(D));
     for (int s = 0; s < 3; ++s) {
@@ -469,8 +469,10 @@ void Net::decode(int b) {
     }
     for (int a = 0; a < na; ++a) { D.anchor_w[a] = ctx->cfg.anchors[a][0]; D.anchor_h[a] = ctx->cfg.anchors[a][1]; }
     D.na = na; D.nc = nc; D.pitch = head_pitch; D.n_total = (int)rows_per_image; D.batch = b;
-    launch_decode(ctx, D, boxes.as<float>());
+    return D;
 }
+
+void Net::decode(int b) { launch_decode(ctx, decode_args(b), boxes.as<float>()); }
 
 std::string Net::profile(int b, int iters) {
     Y3_CHECK(loaded, Y3_ERR_STATE, "weights not loaded");

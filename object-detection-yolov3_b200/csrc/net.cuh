@@ -69,6 +69,7 @@ struct Net {
     void load(int n, const char* const* names, DLManagedTensor* const* tensors);
     void forward(const float* in_dev, int b);   // NCHW fp32 on the device -> heads
     void decode(int b);                         // heads -> boxes
+    DecodeArgs decode_args(int b) const;        // for the fused decode+candidates path
     std::string profile(int b, int iters);      // per-layer CSV report
 
   private:

@@ -25,12 +25,13 @@
 #include "postproc.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <math.h>
 
 namespace y3 {
 
 static constexpr int NMS_T = 512;             // boxes per chunk
 static constexpr int NMS_W = NMS_T / 64;      // mask words per row
-static constexpr int NMS_THREADS = 256;
+static constexpr int NMS_THREADS = 1024;    // mask + apply phases scale with threads; the sweep is one thread
 static constexpr int64_t BIG_SEGMENT = 32768; // segments above this use resolve/apply launches (whole GPU per segment)
 
 // ------------------------------------------------------------------------------------------
@@ -49,41 +50,64 @@ struct KeyLayout {
     uint64_t row_mask;
 };
 
+// IDX = uint32_t when the element count fits (the common case): 64-bit divisions are ~10x slower
+template <typename IDX>
 __global__ void __launch_bounds__(256)
-k_candidates(CandSource src, KeyLayout kl, int64_t total, uint64_t* __restrict__ keys,
+k_candidates(CandSource src, KeyLayout kl, int64_t total, float logit_floor, uint64_t* __restrict__ keys,
              uint32_t* __restrict__ vals, unsigned long long* __restrict__ counter, int64_t cap) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const IDX stride = (IDX)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
     // total is rounded up to a multiple of 32 by the loop bound so that ballots stay converged
-    const int64_t total_r = (total + 31) & ~(int64_t)31;
+    const IDX total_r = (IDX)((total + 31) & ~(int64_t)31);
+    const IDX nc = (IDX)src.nc, rpi = (IDX)src.rows_per_image;
     const float thr = src.score_thr;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total_r; e += stride) {
+    for (IDX e = (IDX)blockIdx.x * blockDim.x + threadIdx.x; e < total_r; e += stride) {
         bool pass = false;
         uint64_t key = 0;
         uint32_t val = 0;
-        if (e < total) {
-            const int64_t grow = e / src.nc;                 // global row = img * rows + row
-            const int c = (int)(e - grow * src.nc);
-            const float p = __ldg(src.cls + grow * src.cls_stride + c);
-            float s;
-            if (src.raw_scores) {
-                s = p;
-                pass = true;
+        if (e < (IDX)total) {
+            const IDX grow = e / nc;                         // global row = img * rows + row
+            const int c = (int)(e - grow * nc);
+            const IDX img = grow / rpi;
+            const IDX row = grow - img * rpi;
+            float s = 0.f;
+            if (src.from_heads) {
+                // fused decode: sigmoid of the objectness / class logits straight from the head (model.py:184-185)
+                int sc, cell, a;
+                const float* hp = head_row(src.dec, (int)img, (int)row, &sc, &cell, &a);
+                const float lo = __ldg(hp + 4), lc = __ldg(hp + 5 + c);
+                // exact conservative pre-filter: score^2 = obj*cls <= min(obj, cls); a logit below
+                // logit(thr^2) - margin cannot reach the threshold, so both sigmoids are skipped
+                if (lo >= logit_floor && lc >= logit_floor) {
+                    const float o = sigmoid_f(lo);
+                    const float p = sigmoid_f(lc);
+                    s = __fsqrt_rn(__fmul_rn(p, o));
+                    pass = (s >= thr);
+                    if (pass && src.filter_small) {
+                        const float w = __fsub_rn(decode_corner(src.dec, hp, sc, cell, a, 2), decode_corner(src.dec, hp, sc, cell, a, 0));
+                        const float h = __fsub_rn(decode_corner(src.dec, hp, sc, cell, a, 3), decode_corner(src.dec, hp, sc, cell, a, 1));
+                        pass = (w > src.min_size) && (h > src.min_size);
+                    }
+                }
             } else {
-                const float o = src.obj ? __ldg(src.obj + grow * src.obj_stride) : 1.0f;
-                s = __fsqrt_rn(__fmul_rn(p, o));             // np.sqrt(class_probs * objectness)
-                pass = (s >= thr);                           // NaN -> false
-            }
-            if (pass && src.filter_small) {
-                const float* b = src.box + grow * src.box_stride;
-                const float w = __fsub_rn(__ldg(b + 2), __ldg(b + 0));
-                const float h = __fsub_rn(__ldg(b + 3), __ldg(b + 1));
-                pass = (w > src.min_size) && (h > src.min_size);
+                const float p = __ldg(src.cls + (int64_t)grow * src.cls_stride + c);
+                if (src.raw_scores) {
+                    s = p;
+                    pass = true;
+                } else {
+                    const float o = src.obj ? __ldg(src.obj + (int64_t)grow * src.obj_stride) : 1.0f;
+                    s = __fsqrt_rn(__fmul_rn(p, o));             // np.sqrt(class_probs * objectness)
+                    pass = (s >= thr);                           // NaN -> false
+                }
+                if (pass && src.filter_small) {
+                    const float* b = src.box + (int64_t)grow * src.box_stride;
+                    const float w = __fsub_rn(__ldg(b + 2), __ldg(b + 0));
+                    const float h = __fsub_rn(__ldg(b + 3), __ldg(b + 1));
+                    pass = (w > src.min_size) && (h > src.min_size);
+                }
             }
             if (pass) {
-                const int64_t img = grow / src.rows_per_image;
-                const int64_t row = grow - img * src.rows_per_image;
-                const uint64_t seg = (uint64_t)(img * src.nc + c);
+                const uint64_t seg = (uint64_t)img * src.nc + (uint64_t)c;
                 key = (seg << kl.seg_shift) | ((uint64_t)(~orderable(s)) << kl.row_bits) | (uint64_t)row;
                 val = (uint32_t)grow;
             }
@@ -107,8 +131,18 @@ k_gather_sorted(CandSource src, const uint32_t* __restrict__ vals, int64_t n, fl
                 float* __restrict__ sarea, uint8_t* __restrict__ supp, uint8_t* __restrict__ keepf) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    const float* b = src.box + (int64_t)vals[p] * src.box_stride;
-    const float4 bx = make_float4(__ldg(b), __ldg(b + 1), __ldg(b + 2), __ldg(b + 3));
+    float4 bx;
+    if (src.from_heads) {
+        const int64_t grow = vals[p];
+        const int64_t img = grow / src.rows_per_image;
+        int sc, cell, a;
+        const float* hp = head_row(src.dec, (int)img, (int)(grow - img * src.rows_per_image), &sc, &cell, &a);
+        bx = make_float4(decode_corner(src.dec, hp, sc, cell, a, 0), decode_corner(src.dec, hp, sc, cell, a, 1),
+                         decode_corner(src.dec, hp, sc, cell, a, 2), decode_corner(src.dec, hp, sc, cell, a, 3));
+    } else {
+        const float* b = src.box + (int64_t)vals[p] * src.box_stride;
+        bx = make_float4(__ldg(b), __ldg(b + 1), __ldg(b + 2), __ldg(b + 3));
+    }
     sbox[p] = bx;
     sarea[p] = box_area_exact(bx);
     supp[p] = 0;
@@ -375,10 +409,29 @@ NmsResult PostProc::run(const CandSource& src, float iou_thr) {
     Y3_CUDA(cudaMemsetAsync(counters.p, 0, 64, st));
 
     {
+        // logit(thr^2) minus a margin far above any rounding of expf / the division (see k_candidates)
+        float logit_floor = -INFINITY;
+        if (src.from_heads && src.score_thr > 0.f && src.score_thr < 1.f) {
+            const double t2 = (double)src.score_thr * (double)src.score_thr;
+            logit_floor = (float)(log(t2 / (1.0 - t2)) - 0.05);
+        }
         const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
-        k_candidates<<<blocks, 256, 0, st>>>(src, kl, total, keys[0].as<uint64_t>(), vals[0].as<uint32_t>(),
-                                             counters.as<unsigned long long>(), cap);
+        cudaEvent_t e0, e1;
+        Y3_CUDA(cudaEventCreate(&e0)); Y3_CUDA(cudaEventCreate(&e1));
+        Y3_CUDA(cudaEventRecord(e0, st));
+        if (total + 32 < (1ll << 32))
+            k_candidates<uint32_t><<<blocks, 256, 0, st>>>(src, kl, total, logit_floor, keys[0].as<uint64_t>(), vals[0].as<uint32_t>(),
+                                                           counters.as<unsigned long long>(), cap);
+        else
+            k_candidates<uint64_t><<<blocks, 256, 0, st>>>(src, kl, total, logit_floor, keys[0].as<uint64_t>(), vals[0].as<uint32_t>(),
+                                                           counters.as<unsigned long long>(), cap);
+        Y3_CUDA(cudaEventRecord(e1, st));
         Y3_LAUNCHED(ctx);
+        Y3_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        last_cand_ms = ms;
     }
     unsigned long long* h_cnt = host_small.as<unsigned long long>();
     Y3_CUDA(cudaMemcpyAsync(h_cnt, counters.p, 8, cudaMemcpyDeviceToHost, st));

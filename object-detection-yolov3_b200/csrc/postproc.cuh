@@ -2,6 +2,7 @@
 // small-box filter + score threshold + compaction -> sort -> exact greedy per-class NMS.
 #pragma once
 #include "common.cuh"
+#include "aux_kernels.cuh"
 
 namespace y3 {
 
@@ -17,6 +18,8 @@ struct CandSource {
     float min_size = 0.f;
     bool raw_scores = false;     // score = cls (single_class_nms entry) instead of sqrt(cls*obj)
     float score_thr = 0.1f;      // ignored when raw_scores
+    bool from_heads = false;     // fused path: decode on the fly from the raw fp32 heads (no decoded tensor)
+    DecodeArgs dec;              // valid when from_heads
 };
 
 // Result lives in PostProc-owned device buffers until the next run().
@@ -35,6 +38,7 @@ struct PostProc {
     DevBuf keys[2], vals[2], sort_tmp, sbox, sarea, supp, keepf, seg_off, counters, blk, kbuf;
     DevBuf o_box, o_score, o_label, o_img, o_src, o_rank;
     PinnedBuf host_small;
+    float last_cand_ms = 0.f;    // device time of the last k_candidates launch (decode+threshold+compaction)
     explicit PostProc(y3_context* c) : ctx(c) {}
     NmsResult run(const CandSource& src, float iou_thr);
     // Ordered compaction support: exclusive per-1024-block offsets of set flags into `blk`
