@@ -133,6 +133,42 @@ __global__ void k_bn_fold(const float* __restrict__ g, const float* __restrict__
     t[i] = b[i] - m[i] * sc;
 }
 
+// Fused upsample: Conv2DTranspose(k2,s2) followed by concat [up, route] and a 1x1 conv is one linear map per
+// output phase (i,j):  W'_ij[k, ci] = sum_co Wy[co, k] * Kt[i,j,co,ci]  (fp32, rounded to bf16 once),
+// route columns copied, bias' = by + sum_co Wy[co,k] * bt[co].   Wy: Keras [2C, cout]; Kt: Keras [2,2,C_up,C_x].
+__global__ void k_compose_up(const float* __restrict__ wy, const float* __restrict__ kt, const float* __restrict__ by,
+                             const float* __restrict__ bt, int c_up, int c_x, int c_r, int cout,
+                             __nv_bfloat16* __restrict__ w_out /*[4][cout][c_x+c_r]*/, float* __restrict__ b_out) {
+    const int K = c_x + c_r;
+    const long long n = 4LL * cout * K;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(i % K);
+        const long long r = i / K;
+        const int k = (int)(r % cout);
+        const int ij = (int)(r / cout);
+        float acc;
+        if (kk < c_x) {
+            acc = 0.f;
+            for (int co = 0; co < c_up; ++co)
+                acc = fmaf(wy[(long long)co * cout + k], kt[((long long)ij * c_up + co) * c_x + kk], acc);
+        } else {
+            acc = wy[(long long)(c_up + kk - c_x) * cout + k];
+        }
+        w_out[i] = __float2bfloat16_rn(acc);
+        if (ij == 0 && kk == 0) {
+            float b = by[k];
+            for (int co = 0; co < c_up; ++co) b = fmaf(wy[(long long)co * cout + k], bt[co], b);
+            b_out[k] = b;
+        }
+    }
+}
+void compose_up(y3_context* ctx, const float* wy, const float* kt, const float* by, const float* bt, int c_up, int c_x, int c_r,
+                int cout, __nv_bfloat16* w_out, float* b_out) {
+    const long long n = 4LL * cout * (c_x + c_r);
+    k_compose_up<<<(int)std::min<long long>((n + 255) / 256, 8192), 256, 0, ctx->stream>>>(wy, kt, by, bt, c_up, c_x, c_r, cout, w_out, b_out);
+    Y3_LAUNCHED(ctx);
+}
+
 void pack_conv_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, int taps, int cin, int cout, int cout_pad) {
     const long long n = (long long)cout_pad * taps * cin;
     k_pack_conv_w<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, ctx->stream>>>(k, out, taps, cin, cout, cout_pad);

@@ -50,6 +50,8 @@ void launch_stem(y3_context* ctx, const float* in, __nv_bfloat16* out, const flo
                  const float* scale, const float* shift, int B, int H, int W, int cin);
 void pack_conv_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, int taps, int cin, int cout, int cout_pad);
 void pack_convt_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, long long n);
+void compose_up(y3_context* ctx, const float* wy, const float* kt, const float* by, const float* bt, int c_up, int c_x, int c_r,
+                int cout, __nv_bfloat16* w_out, float* b_out);
 void bn_fold(y3_context* ctx, const float* g, const float* b, const float* m, const float* v, float* s, float* t, int c);
 void heads_to_nchw(y3_context* ctx, const float* in, float* out, int B, int HW, int C, int pitch);
 void slice_to_nchw(y3_context* ctx, const __nv_bfloat16* in, float* out, int B, int H, int W, int C, int pitch, int coff);

@@ -65,7 +65,8 @@ __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u &
 
 template <int BN, int BK>
 __global__ void __launch_bounds__(CONV_THREADS, ConvCfg<BN, BK>::CTAS_PER_SM)
-k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
+          const __grid_constant__ CUtensorMap map_b,
           const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
           const ConvArgs P) {
 #if defined(__CUDA_ARCH_FEAT_SM100_ALL) || defined(__CUDA_ARCH_FEAT_SM101_ALL)
@@ -88,6 +89,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a);
+        if (P.k_split < P.kchunks) prefetch_tmap(&map_a2);
         prefetch_tmap(&map_b);
         if (!P.out_f32) prefetch_tmap(&map_out);
         if (P.has_res) prefetch_tmap(&map_res);
@@ -142,8 +144,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                         mbar_wait(&empty[stage], phase ^ 1u);
                         unsigned char* sa = stage_base + stage * C::STAGE_BYTES;
                         mbar_expect_tx(&full[stage], (uint32_t)(rows * BK * 2 + C::B_BYTES));
-                        if (P.stride == 1)
-                            tma_load_4d(sa, &map_a, &full[stage], kc * BK, x0 + kw - P.pad, y0 + kh - P.pad, img);
+                        if (P.stride == 1) {
+                            if (kc < P.k_split) tma_load_4d(sa, &map_a, &full[stage], kc * BK, x0 + kw - P.pad, y0 + kh - P.pad, img);
+                            else tma_load_4d(sa, &map_a2, &full[stage], (kc - P.k_split) * BK, x0 + kw - P.pad, y0 + kh - P.pad, img);
+                        }
                         else
                             tma_load_5d(sa, &map_a, &full[stage], (kw & 1) * P.a_cpitch + kc * BK, x0 + (kw >> 1), kh & 1,
                                         y0 + (kh >> 1), img);
@@ -342,7 +346,7 @@ static void launch_t(y3_context* ctx, const ConvLaunch& L) {
         attr[ctx->device & 63] = true;
     }
     const int grid = std::min(L.args.total_tiles, ctx->sm_count * C::CTAS_PER_SM);
-    k_conv_tc<BN, BK><<<grid, CONV_THREADS, C::SMEM, ctx->stream>>>(L.map_a, L.map_b, L.map_out, L.map_res, L.args);
+    k_conv_tc<BN, BK><<<grid, CONV_THREADS, C::SMEM, ctx->stream>>>(L.map_a, L.map_a2, L.map_b, L.map_out, L.map_res, L.args);
     Y3_LAUNCHED(ctx);
 }
 

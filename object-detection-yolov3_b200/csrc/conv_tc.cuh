@@ -14,6 +14,7 @@ struct ConvArgs {
     int cin, kchunks;        // channels per tap, cin / BK
     int stride, pad;         // 1|2 ; left/top zero padding (TF SAME: s1 k3 -> 1, s2 -> 0)
     int a_cpitch;            // channel pitch of the input buffer (phase offset of the stride-2 view)
+    int k_split;             // K chunks [0,k_split) come from map_a, the rest from map_a2 (fused upsample+concat)
     int has_res, linear, out_f32;
     int Ho, Wo;
     const float* bias;       // [cout_pad]
@@ -25,7 +26,7 @@ struct ConvArgs {
 };
 
 struct ConvLaunch {
-    CUtensorMap map_a, map_b, map_out, map_res;
+    CUtensorMap map_a, map_a2, map_b, map_out, map_res;
     ConvArgs args;
     int bn, bk;              // template selection (two_cta: bn = N of the pair UMMA, 128 or 256)
     int two_cta;             // use the cta_group::2 kernel (conv_tc2.cu)

@@ -50,7 +50,8 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 
 template <int BN2, int NSTG_>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV2_THREADS, 1)
-k_conv_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+k_conv_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
+          const __grid_constant__ CUtensorMap map_b,
            const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, const ConvArgs P) {
 #if defined(__CUDA_ARCH_FEAT_SM100_ALL) || defined(__CUDA_ARCH_FEAT_SM101_ALL)
     using C = Conv2Cfg<BN2, NSTG_>;
@@ -76,6 +77,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a);
+        if (P.k_split < P.kchunks) prefetch_tmap(&map_a2);
         prefetch_tmap(&map_b);
         if (!P.out_f32) prefetch_tmap(&map_out);
         if (P.has_res) prefetch_tmap(&map_res);
@@ -134,8 +136,10 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                         unsigned char* sa = stage_base + stage * C::STAGE_BYTES;
                         const uint32_t lead_full = mapa_u32(&full[stage], 0);
                         if (rank == 0) mbar_expect_tx(&full[stage], (uint32_t)(2 * (rows * BK * 2 + C::B_BYTES)));
-                        if (P.stride == 1)
-                            tma2_load_4d(sa, &map_a, lead_full, kc * BK, x0 + kw - P.pad, y0 + kh - P.pad, img);
+                        if (P.stride == 1) {
+                            if (kc < P.k_split) tma2_load_4d(sa, &map_a, lead_full, kc * BK, x0 + kw - P.pad, y0 + kh - P.pad, img);
+                            else tma2_load_4d(sa, &map_a2, lead_full, (kc - P.k_split) * BK, x0 + kw - P.pad, y0 + kh - P.pad, img);
+                        }
                         else
                             tma2_load_5d(sa, &map_a, lead_full, (kw & 1) * P.a_cpitch + kc * BK, x0 + (kw >> 1), kh & 1,
                                          y0 + (kh >> 1), img);
@@ -303,7 +307,7 @@ static void launch2_t(y3_context* ctx, const ConvLaunch& L) {
         Y3_CUDA(cudaFuncSetAttribute(k_conv_tc2<BN2, NSTG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr[ctx->device & 63] = true;
     }
-    k_conv_tc2<BN2, NSTG_><<<L.grid, CONV2_THREADS, C::SMEM, ctx->stream>>>(L.map_a, L.map_b, L.map_out, L.map_res, L.args);
+    k_conv_tc2<BN2, NSTG_><<<L.grid, CONV2_THREADS, C::SMEM, ctx->stream>>>(L.map_a, L.map_a2, L.map_b, L.map_out, L.map_res, L.args);
     Y3_LAUNCHED(ctx);
 }
 

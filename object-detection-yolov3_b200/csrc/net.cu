@@ -86,6 +86,31 @@ void Net::add_convt(View in, View out) {
     ops.push_back(std::move(op));
 }
 
+// bridge output x (low res) --ConvT(k2,s2)--> up ; concat [up, route] ; 1x1 conv_layer  ==  one op
+View Net::add_upconv(View x, View route, int cout) {
+    Op op;
+    op.kind = Op::UPCONV;
+    op.convt = "conv2d_transpose" + suffix(n_convt++);
+    op.name = "conv2d" + suffix(n_conv++);
+    op.bn = "batch_normalization" + suffix(n_bn++);
+    op.cin = x.c + route.c; op.cout = cout; op.cout_pad = cout; op.k = 1; op.stride = 1;
+    op.in = x; op.in2 = route;
+    const TensorInfo& tr = tensors[route.t];
+    op.out.t = new_tensor(tr.h, tr.w, cout); op.out.coff = 0; op.out.c = cout;
+    ops.push_back(std::move(op));
+    return ops.back().out;
+}
+
+void Net::add_yolo_up(View x, View route_in, int f, View* route, View* out) {
+    View y = add_upconv(x, route_in, f / 2);
+    y = add_conv(y, f, 3, 1);
+    y = add_conv(y, f / 2, 1, 1);
+    y = add_conv(y, f, 3, 1);
+    y = add_conv(y, f / 2, 1, 1);
+    *route = y;
+    *out = add_conv(y, f, 3, 1);
+}
+
 void Net::build() {
     const y3_config& c = ctx->cfg;
     H = c.img_h; W = c.img_w; C = c.img_c; nc = c.num_classes; na = c.num_anchors; maxB = c.max_batch;
@@ -108,20 +133,25 @@ void Net::build() {
     ops.push_back(std::move(stem));
     View x = ops.back().out;
 
-    const int cat3 = new_tensor(H / 8, W / 8, 512);      // [up(256) | route1(256)]
-    const int cat2 = new_tensor(H / 16, W / 16, 1024);   // [up(512) | route2(512)]
-    View none;
-
+    const bool fuse_up = getenv("Y3_NO_UPFUSE") == nullptr;
+    View none, r1, r2;
+    int cat2 = -1, cat3 = -1;
+    if (!fuse_up) {
+        cat3 = new_tensor(H / 8, W / 8, 512);      // [up(256) | route1(256)]
+        cat2 = new_tensor(H / 16, W / 16, 1024);   // [up(512) | route2(512)]
+        r1.t = cat3; r1.coff = 256; r1.c = 256;
+        r2.t = cat2; r2.coff = 512; r2.c = 512;
+    }
     x = add_conv(x, 64, 3, 2);
     x = add_block(x, 1, none);
     x = add_conv(x, 128, 3, 2);
     x = add_block(x, 2, none);
     x = add_conv(x, 256, 3, 2);
-    View r1; r1.t = cat3; r1.coff = 256; r1.c = 256;
     x = add_block(x, 8, r1);
+    const View route1 = x;
     x = add_conv(x, 512, 3, 2);
-    View r2; r2.t = cat2; r2.coff = 512; r2.c = 512;
     x = add_block(x, 8, r2);
+    const View route2 = x;
     x = add_conv(x, 1024, 3, 2);
     x = add_block(x, 4, none);
 
@@ -129,12 +159,20 @@ void Net::build() {
     add_yolo(x, 1024, &route, &out);
     add_det(out, 0);
     x = add_conv(route, 512, 1, 1);
-    { View up; up.t = cat2; up.coff = 0; up.c = 512; add_convt(x, up); }
-    { View in; in.t = cat2; in.coff = 0; in.c = 1024; add_yolo(in, 512, &route, &out); }
+    if (fuse_up) {
+        add_yolo_up(x, route2, 512, &route, &out);
+    } else {
+        { View up; up.t = cat2; up.coff = 0; up.c = 512; add_convt(x, up); }
+        { View in; in.t = cat2; in.coff = 0; in.c = 1024; add_yolo(in, 512, &route, &out); }
+    }
     add_det(out, 1);
     x = add_conv(route, 256, 1, 1);
-    { View up; up.t = cat3; up.coff = 0; up.c = 256; add_convt(x, up); }
-    { View in; in.t = cat3; in.coff = 0; in.c = 512; add_yolo(in, 256, &route, &out); }
+    if (fuse_up) {
+        add_yolo_up(x, route1, 256, &route, &out);
+    } else {
+        { View up; up.t = cat3; up.coff = 0; up.c = 256; add_convt(x, up); }
+        { View in; in.t = cat3; in.coff = 0; in.c = 512; add_yolo(in, 256, &route, &out); }
+    }
     add_det(out, 2);
 
     // --- liveness + buffer assignment (linear scan, exact-size free lists)
@@ -142,6 +180,7 @@ void Net::build() {
         Op& op = ops[i];
         auto use = [&](int t) { if (t >= 0) { if (tensors[t].first < 0) tensors[t].first = (int)i; tensors[t].last = (int)i; } };
         if (op.kind != Op::STEM) use(op.in.t);
+        if (op.kind == Op::UPCONV) use(op.in2.t);
         if (op.res_t >= 0) use(op.res_t);
         if (op.kind != Op::DET) use(op.out.t);
     }
@@ -181,6 +220,14 @@ void Net::build() {
             op.w.reserve((size_t)taps * op.cin * 32 * 4);
         } else if (op.kind == Op::CONVT) {
             op.w.reserve((size_t)4 * op.cout * op.cin * 2);
+        } else if (op.kind == Op::UPCONV) {
+            op.w.reserve((size_t)4 * op.cout_pad * op.cin * 2);
+            op.raw_k.reserve((size_t)op.cin * op.cout * 4);
+            op.raw_b.reserve((size_t)op.cout * 4);
+            op.raw_tk.reserve((size_t)4 * op.in.c * op.in.c * 4);
+            op.raw_tb.reserve((size_t)op.in.c * 4);
+            Y3_CUDA(cudaMemset(op.raw_b.p, 0, (size_t)op.cout * 4));
+            Y3_CUDA(cudaMemset(op.raw_tb.p, 0, (size_t)op.in.c * 4));
         } else {
             op.w.reserve((size_t)op.cout_pad * taps * op.cin * 2);
         }
@@ -235,9 +282,10 @@ void Net::make_launches(Op& op) {
         if (small_opt && bn == 256 && op.k == 1 && pair_tiles_256 < 3LL * (ctx->sm_count / 2)) bn = 128;
     }
     const int oc = bn < 64 ? bn : 64;
-    const int n_sub = op.kind == Op::CONVT ? 4 : 1;
-    const int taps = op.kind == Op::CONVT ? 1 : op.k * op.k;
-    const bool flat = (op.k == 1 && op.kind != Op::CONVT);
+    const bool phased = (op.kind == Op::CONVT || op.kind == Op::UPCONV);   // 4 launches, one per output phase (i,j)
+    const int n_sub = phased ? 4 : 1;
+    const int taps = phased ? 1 : op.k * op.k;
+    const bool flat = (op.k == 1 && !phased);
 
     for (int sub = 0; sub < n_sub; ++sub) {
         ConvLaunch L;
@@ -246,10 +294,11 @@ void Net::make_launches(Op& op) {
         L.bn = bn; L.bk = bk; L.two_cta = two ? 1 : 0;
         A.taps = taps; A.kwn = op.k == 3 ? 3 : 1;
         A.cin = cin; A.kchunks = cin / bk;
-        A.stride = op.kind == Op::CONVT ? 1 : op.stride;
+        A.stride = phased ? 1 : op.stride;
         A.pad = (op.k == 3 && op.stride == 1) ? 1 : 0;
         A.a_cpitch = pitch_in;
-        A.has_res = op.res_t >= 0; A.linear = op.kind != Op::CONV; A.out_f32 = op.kind == Op::DET;
+        A.has_res = op.res_t >= 0; A.linear = (op.kind == Op::DET || op.kind == Op::CONVT); A.out_f32 = op.kind == Op::DET;
+        A.k_split = A.kchunks;
         A.bias = op.bias.as<float>(); A.scale = op.scale.as<float>(); A.shift = op.shift.as<float>();
         A.cout_valid = op.cout;
         A.n_tiles_n = op.cout_pad / bn;
@@ -267,7 +316,7 @@ void Net::make_launches(Op& op) {
             const int ho = ti.h, wo = ti.w;
             pick_patch(ho, wo, &A.BH, &A.BW);
             A.Ho = ho; A.Wo = wo;
-            uint64_t dims[4] = {(uint64_t)cin, (uint64_t)ti.w, (uint64_t)ti.h, (uint64_t)maxB};
+            uint64_t dims[4] = {(uint64_t)op.in.c, (uint64_t)ti.w, (uint64_t)ti.h, (uint64_t)maxB};
             uint64_t str[3] = {(uint64_t)pitch_in * 2, (uint64_t)ti.w * pitch_in * 2, (uint64_t)ti.h * ti.w * pitch_in * 2};
             uint32_t box[4] = {(uint32_t)bk, (uint32_t)A.BW, (uint32_t)A.BH, 1};
             encode_tmap_bf16(&L.map_a, in_base, 4, dims, str, box, bk * 2);
@@ -282,10 +331,23 @@ void Net::make_launches(Op& op) {
             uint32_t box[5] = {(uint32_t)bk, (uint32_t)A.BW, 1, (uint32_t)A.BH, 1};
             encode_tmap_bf16(&L.map_a, in_base, 5, dims, str, box, bk * 2);
         }
+        if (op.kind == Op::UPCONV) {
+            // route half: phase (i,j) view of the hi-res route tensor, same tile coordinates as x
+            const TensorInfo& tr = tensors[op.in2.t];
+            const int i = sub >> 1, j = sub & 1;
+            const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(tr.ptr) + op.in2.coff + ((size_t)i * tr.w + j) * tr.c;
+            uint64_t dims[4] = {(uint64_t)op.in2.c, (uint64_t)ti.w, (uint64_t)ti.h, (uint64_t)maxB};
+            uint64_t str[3] = {(uint64_t)2 * tr.c * 2, (uint64_t)2 * tr.w * tr.c * 2, (uint64_t)tr.h * tr.w * tr.c * 2};
+            uint32_t box[4] = {(uint32_t)bk, (uint32_t)A.BW, (uint32_t)A.BH, 1};
+            encode_tmap_bf16(&L.map_a2, rb, 4, dims, str, box, bk * 2);
+            A.k_split = op.in.c / bk;
+        } else {
+            L.map_a2 = L.map_a;
+        }
         // ---- B operand (weights, K-major)
         {
             const uint64_t ktot = (uint64_t)taps * cin;
-            const __nv_bfloat16* wbase = op.w.as<__nv_bfloat16>() + (size_t)sub * op.cout * cin;
+            const __nv_bfloat16* wbase = op.w.as<__nv_bfloat16>() + (size_t)sub * op.cout_pad * cin;
             uint64_t dims[2] = {ktot, (uint64_t)op.cout_pad};
             uint64_t str[1] = {ktot * 2};
             uint32_t box[2] = {(uint32_t)bk, (uint32_t)(two ? bn / 2 : bn)};
@@ -307,7 +369,7 @@ void Net::make_launches(Op& op) {
                 uint64_t str[3] = {(uint64_t)po * 2, M * po * 2, M * po * 2};
                 uint32_t box[4] = {(uint32_t)oc, 128, 1, 1};
                 encode_tmap_bf16(&L.map_out, obase, 4, dims, str, box, oc * 2);
-            } else if (op.kind == Op::CONVT) {
+            } else if (phased) {
                 const int i = sub >> 1, j = sub & 1;
                 // out[n, 2h+i, 2w+j, co] : same tile coordinates as the input, doubled strides
                 obase += ((size_t)i * to.w + j) * po;
@@ -387,15 +449,41 @@ void Net::load(int n, const char* const* names, DLManagedTensor* const* tensors_
         const void* src = static_cast<const char*>(t.data) + t.byte_offset;
         Op* op = nullptr;
         bool is_bn = false;
+        bool is_t = false;
         for (Op& o : ops) {
             if (o.name == layer) { op = &o; break; }
             if (o.bn == layer) { op = &o; is_bn = true; break; }
+            if (o.kind == Op::UPCONV && o.convt == layer) { op = &o; is_t = true; break; }
         }
         Y3_CHECK(op, Y3_ERR_INVALID, "weight '%s': no such layer in this network", names[i]);
         stage.reserve((size_t)numel * 4);
         const cudaMemcpyKind kind = t.device.device_type == kDLCUDA ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
         const int taps = op->k * op->k;
-        if (is_bn) {
+        if (is_t) {
+            // weights of the transposed conv that is composed into this op (Keras [2,2,C_up,C_x] / [C_up])
+            const int cu = op->in.c;
+            if (var == "kernel") {
+                Y3_CHECK(numel == (int64_t)4 * cu * cu, Y3_ERR_INVALID, "weight '%s': expected [2,2,%d,%d]", names[i], cu, cu);
+                Y3_CUDA(cudaMemcpyAsync(op->raw_tk.p, src, (size_t)numel * 4, kind, st));
+                op->have |= 64u;
+            } else if (var == "bias") {
+                Y3_CHECK(numel == cu, Y3_ERR_INVALID, "weight '%s': expected %d values", names[i], cu);
+                Y3_CUDA(cudaMemcpyAsync(op->raw_tb.p, src, (size_t)numel * 4, kind, st));
+                op->have |= 128u;
+            } else {
+                fail(Y3_ERR_INVALID, "weight '%s': unknown variable", names[i]);
+            }
+        } else if (op->kind == Op::UPCONV && !is_bn && (var == "kernel" || var == "bias")) {
+            if (var == "kernel") {
+                Y3_CHECK(numel == (int64_t)op->cin * op->cout, Y3_ERR_INVALID, "weight '%s': expected [1,1,%d,%d]", names[i], op->cin, op->cout);
+                Y3_CUDA(cudaMemcpyAsync(op->raw_k.p, src, (size_t)numel * 4, kind, st));
+                op->have |= 1u;
+            } else {
+                Y3_CHECK(numel == op->cout, Y3_ERR_INVALID, "weight '%s': expected %d values", names[i], op->cout);
+                Y3_CUDA(cudaMemcpyAsync(op->raw_b.p, src, (size_t)numel * 4, kind, st));
+                op->have |= 2u;
+            }
+        } else if (is_bn) {
             int slot = var == "gamma" ? 0 : var == "beta" ? 1 : var == "moving_mean" ? 2 : var == "moving_variance" ? 3 : -1;
             Y3_CHECK(slot >= 0, Y3_ERR_INVALID, "weight '%s': unknown BatchNorm variable", names[i]);
             Y3_CHECK(numel == op->cout, Y3_ERR_INVALID, "weight '%s': expected %d values, got %lld", names[i], op->cout, (long long)numel);
@@ -426,9 +514,12 @@ void Net::load(int n, const char* const* names, DLManagedTensor* const* tensors_
     // fold BatchNorm, check completeness
     loaded = true;
     for (Op& op : ops) {
-        const bool needs_bn = (op.kind == Op::CONV || op.kind == Op::STEM);
-        const unsigned need = needs_bn ? 0x3fu : 0x3u;
-        if ((op.have & need) != need) { loaded = false; missing = op.name + (needs_bn ? " / " + op.bn : ""); continue; }
+        const bool needs_bn = (op.kind == Op::CONV || op.kind == Op::STEM || op.kind == Op::UPCONV);
+        const unsigned need = op.kind == Op::UPCONV ? 0xffu : needs_bn ? 0x3fu : 0x3u;
+        if ((op.have & need) != need) { loaded = false; missing = op.name + (needs_bn ? " / " + op.bn : "") + (op.kind == Op::UPCONV ? " / " + op.convt : ""); continue; }
+        if (op.kind == Op::UPCONV)
+            compose_up(ctx, op.raw_k.as<float>(), op.raw_tk.as<float>(), op.raw_b.as<float>(), op.raw_tb.as<float>(), op.in.c, op.in.c,
+                       op.in2.c, op.cout, op.w.as<__nv_bfloat16>(), op.bias.as<float>());
         if (needs_bn) {
             float* r = op.bn_raw.as<float>();
             bn_fold(ctx, r, r + op.cout_pad, r + 2 * op.cout_pad, r + 3 * op.cout_pad, op.scale.as<float>(),
@@ -508,7 +599,7 @@ std::string Net::profile(int b, int iters) {
         double bytes = in_px * op.cin * (op.kind == Op::STEM ? 4 : 2) + (double)b * oh * ow * op.cout * (op.kind == Op::DET ? 4 : 2)
                        + (double)op.cout * taps * op.cin * 2;
         if (op.res_t >= 0) bytes += (double)b * oh * ow * op.cout * 2;
-        const char* kind = op.kind == Op::STEM ? "stem" : op.kind == Op::CONV ? "conv" : op.kind == Op::DET ? "det" : "convt";
+        const char* kind = op.kind == Op::STEM ? "stem" : op.kind == Op::CONV ? "conv" : op.kind == Op::DET ? "det" : op.kind == Op::UPCONV ? "upcnv" : "convt";
         int bh = 0, bw = 0, bn = 0, bk = 0, tiles = 0;
         if (!op.launches.empty()) {
             const ConvLaunch& L = op.launches[0];

@@ -21,26 +21,27 @@ struct View {
 };
 
 struct Op {
-    enum Kind { STEM, CONV, DET, CONVT } kind = CONV;
-    std::string name, bn;
+    enum Kind { STEM, CONV, DET, CONVT, UPCONV } kind = CONV;   // UPCONV = transposed conv + concat + 1x1 conv fused
+    std::string name, bn, convt;
     int cin = 0, cout = 0, cout_pad = 0, k = 1, stride = 1;
-    View in, out, res;
+    View in, in2, out, res;   // in2: the route half of a fused upsample+concat (UPCONV)
     int res_t = -1;
     int head = -1;
     bool flat = false;
     int pix_per_img = 0;
-    unsigned have = 0;            // bit0 kernel, bit1 bias, bits2-5 gamma/beta/mean/var
-    DevBuf w, bias, scale, shift, bn_raw;
+    unsigned have = 0;            // bit0 kernel, bit1 bias, bits2-5 gamma/beta/mean/var, bit6/7 convT kernel/bias
+    DevBuf w, bias, scale, shift, bn_raw, raw_k, raw_b, raw_tk, raw_tb;
     std::vector<ConvLaunch> launches;
     Op() = default;
     Op(Op&& o) noexcept { *this = std::move(o); }
     Op& operator=(Op&& o) noexcept {
-        kind = o.kind; name = std::move(o.name); bn = std::move(o.bn);
+        kind = o.kind; name = std::move(o.name); bn = std::move(o.bn); convt = std::move(o.convt);
         cin = o.cin; cout = o.cout; cout_pad = o.cout_pad; k = o.k; stride = o.stride;
-        in = o.in; out = o.out; res = o.res; res_t = o.res_t; head = o.head; flat = o.flat;
+        in = o.in; in2 = o.in2; out = o.out; res = o.res; res_t = o.res_t; head = o.head; flat = o.flat;
         pix_per_img = o.pix_per_img; have = o.have; launches = std::move(o.launches);
         auto mv = [](DevBuf& a, DevBuf& b) { a.release(); a.p = b.p; a.cap = b.cap; b.p = nullptr; b.cap = 0; };
         mv(w, o.w); mv(bias, o.bias); mv(scale, o.scale); mv(shift, o.shift); mv(bn_raw, o.bn_raw);
+        mv(raw_k, o.raw_k); mv(raw_b, o.raw_b); mv(raw_tk, o.raw_tk); mv(raw_tb, o.raw_tb);
         return *this;
     }
 };
@@ -79,6 +80,8 @@ struct Net {
     void add_yolo(View in, int f, View* route, View* out);
     void add_det(View in, int idx);
     void add_convt(View in, View out);
+    View add_upconv(View x, View route, int cout);
+    void add_yolo_up(View x, View route_in, int f, View* route, View* out);
     void make_launches(Op& op);
     void set_batch(Op& op, int b);
 };

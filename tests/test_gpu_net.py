@@ -32,8 +32,13 @@ def test_layers_small_net():
     want = ora.feature_maps(x)
     got = eng.forward_heads(x.numpy())
     report = []
+    from yolo3_b200 import Y3Error
     for name, ref in ora.trace.items():
-        out = eng.debug_layer_output(name, 2)
+        try:
+            out = eng.debug_layer_output(name, 2)
+        except Y3Error:
+            assert name.startswith("conv2d_transpose")      # composed into its consumer conv: no tensor of its own
+            continue
         err = mt.heads_rel_err(out, ref.numpy())
         report.append((name, tuple(ref.shape), err))
     bad = [r for r in report if not r[2] < 3e-2]
@@ -44,8 +49,9 @@ def test_layers_small_net():
 
 
 TAIL_NOTE = ("bf16 storage of the fm3 tail: the all-ones upsample makes the last ~7 layers 8x more sensitive to "
-             "rounding than the backbone; emulated bf16 gives 0.9-2.4 % on fm3 depending on the weight seed "
-             "(DESIGN.md 'numerics').  Tracked: fuse the transposed conv into its consumer.")
+             "rounding than the backbone.  Measured on B200 over 3 weight draws (tests/head_error_sweep.py): this "
+             "2-anchor / 1-class family gives fm3 = 0.7 %, 2.0 %, 2.2 %; the 3-anchor configs give 0.96-1.24 %.  "
+             "Matches the CPU bf16 emulation of the oracle (DESIGN.md 'numerics') - inherent to bf16, not a kernel fault.")
 
 
 @pytest.mark.parametrize("cfg", [((416, 416, 3), 80, None, 1), ((512, 512, 1), 1, None, 2),
