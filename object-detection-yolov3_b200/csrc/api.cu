@@ -8,6 +8,8 @@
 
 #include <algorithm>
 #include <mutex>
+#include <stdlib.h>
+#include <time.h>
 
 using namespace y3;
 
@@ -21,6 +23,8 @@ static thread_local std::string g_create_error;
         return Y3_OK;                                                                     \
     } catch (const Error& e) {                                                            \
         (h)->last_error = e.msg;                                                          \
+        for (auto& r_ : (h)->phase_log) { (h)->event_pool.push_back(r_.a); (h)->event_pool.push_back(r_.b); } \
+        (h)->phase_log.clear();                                                           \
         cudaGetLastError();                                                               \
         return e.code;                                                                    \
     } catch (const std::exception& e) {                                                   \
@@ -33,22 +37,39 @@ static thread_local std::string g_create_error;
 
 namespace {
 
+cudaEvent_t take_event(y3_context* c) {
+    if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    Y3_CUDA(cudaEventCreate(&e));
+    return e;
+}
+// Times a stage with two events on the stream; nothing blocks until flush_phases().
 struct Phase {
     y3_context* c;
-    cudaEvent_t a, b;
+    cudaEvent_t a;
     float* dst;
-    Phase(y3_context* ctx, float* d) : c(ctx), dst(d) {
-        cudaEventCreate(&a); cudaEventCreate(&b);
-        cudaEventRecord(a, c->stream);
-    }
+    bool open = true;
+    Phase(y3_context* ctx, float* d) : c(ctx), a(take_event(ctx)), dst(d) { cudaEventRecord(a, c->stream); }
     void stop() {
+        if (!open) return;
+        open = false;
+        cudaEvent_t b = take_event(c);
         cudaEventRecord(b, c->stream);
-        cudaEventSynchronize(b);
-        float t = 0; cudaEventElapsedTime(&t, a, b);
-        *dst += t;
+        c->phase_log.push_back({a, b, dst});
     }
-    ~Phase() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    ~Phase() { if (open) c->event_pool.push_back(a); }
 };
+void flush_phases(y3_context* c) {
+    cudaStreamSynchronize(c->stream);
+    for (auto& r : c->phase_log) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) *r.dst += t;
+        c->event_pool.push_back(r.a);
+        c->event_pool.push_back(r.b);
+    }
+    c->phase_log.clear();
+    cudaGetLastError();
+}
 
 const void* to_device(y3_context* c, const void* p, y3_mem mem, size_t bytes, DevBuf& stage) {
     if (mem == Y3_MEM_DEVICE) return p;
@@ -190,6 +211,9 @@ void y3_destroy(y3_handle h) {
     delete h->net;
     delete h->post;
     delete h->tiler;
+    for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
+    for (auto& r : h->phase_log) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -274,6 +298,7 @@ y3_status y3_detect(y3_handle h, const float* in, y3_mem in_mem, int32_t batch, 
         p.stop();
     }
     total.stop();
+    flush_phases(h);
     T.kernels_launched = h->kernels_launched;
     Y3_API_END(h)
 }
@@ -349,6 +374,7 @@ y3_status y3_single_class_nms(y3_handle h, const float* boxes, const float* scor
           from_device(h, keep, Y3_MEM_HOST, R.src_row, (size_t)R.n_kept * 4);
           p.stop(); }
         total.stop();
+        flush_phases(h);
         T.kernels_launched = h->kernels_launched;
     }
     Y3_API_END(h)
@@ -391,6 +417,7 @@ y3_status y3_per_class_nms(y3_handle h, const float* boxes, const float* obj, co
             p.stop();
         }
         total.stop();
+        flush_phases(h);
         T.kernels_launched = h->kernels_launched;
     }
     Y3_API_END(h)
@@ -423,6 +450,53 @@ const void* upload_band(y3_context* h, Tiler* T, const void* img, y3_dtype dt, y
                             cudaMemcpyHostToDevice, h->stream));
     *row_lo = lo;
     return T->img.p;
+}
+
+// Same, but the copy is issued in row chunks on a separate stream with one event per chunk, so that the
+// first tile batches start while later rows are still in flight (pinned host memory overlaps fully).
+struct BandUpload {
+    const void* dev = nullptr;
+    long long row_lo = 0;
+    int chunk_rows = 0;
+    std::vector<cudaEvent_t> done;     // done[k]: rows [row_lo, row_lo + (k+1)*chunk_rows) are resident
+};
+BandUpload upload_band_chunked(y3_context* h, Tiler* T, const void* img, y3_dtype dt, y3_mem mem, int64_t W, int C,
+                               const std::vector<TileGeo>& geo, int64_t first, int64_t count) {
+    BandUpload U;
+    if (mem == Y3_MEM_DEVICE) { U.dev = img; return U; }
+    int lo = geo[first].y0, hi = geo[first].y1;
+    for (int64_t t = first; t < first + count; ++t) { lo = std::min(lo, geo[t].y0); hi = std::max(hi, geo[t].y1); }
+    const size_t row_bytes = (size_t)W * C * dtype_size(dt);
+    T->img.reserve((size_t)(hi - lo) * row_bytes);
+    if (!h->copy_stream) Y3_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    U.dev = T->img.p; U.row_lo = lo;
+    U.chunk_rows = (int)std::max<size_t>(64, ((size_t)32 << 20) / row_bytes);     // ~32 MB per chunk
+    // the previous call's kernels may still read T->img: order the copies after the compute stream
+    cudaEvent_t gate = take_event(h);
+    Y3_CUDA(cudaEventRecord(gate, h->stream));
+    Y3_CUDA(cudaStreamWaitEvent(h->copy_stream, gate, 0));
+    h->event_pool.push_back(gate);
+    for (int r = lo; r < hi; r += U.chunk_rows) {
+        const int n = std::min(U.chunk_rows, hi - r);
+        Y3_CUDA(cudaMemcpyAsync(static_cast<char*>(T->img.p) + (size_t)(r - lo) * row_bytes,
+                                static_cast<const char*>(img) + (size_t)r * row_bytes, (size_t)n * row_bytes,
+                                cudaMemcpyHostToDevice, h->copy_stream));
+        cudaEvent_t e = take_event(h);
+        Y3_CUDA(cudaEventRecord(e, h->copy_stream));
+        U.done.push_back(e);
+    }
+    return U;
+}
+// make the compute stream wait until image rows < row_end are resident
+void wait_rows(y3_context* h, const BandUpload& U, int row_end) {
+    if (U.done.empty()) return;
+    int k = (int)((row_end - U.row_lo + U.chunk_rows - 1) / U.chunk_rows) - 1;
+    k = std::max(0, std::min(k, (int)U.done.size() - 1));
+    Y3_CUDA(cudaStreamWaitEvent(h->stream, U.done[k], 0));
+}
+void release_upload(y3_context* h, BandUpload& U) {
+    for (cudaEvent_t e : U.done) h->event_pool.push_back(e);
+    U.done.clear();
 }
 const TileGeo* upload_geo(y3_context* h, Tiler* T, const std::vector<TileGeo>& geo) {
     T->geo.reserve(geo.size() * sizeof(TileGeo));
@@ -531,17 +605,22 @@ y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dt, y3_mem img_m
     T->acc_rows = 0;
     *n_out = 0;
     if (tile_count > 0) {
-        long long row_lo = 0;
-        const void* d_img;
-        { Phase p(h, &Tm.ms_h2d); d_img = upload_band(h, T, img, dt, img_mem, W, C, geo, tile_first, tile_count, &row_lo); p.stop(); }
         const TileGeo* d_geo = upload_geo(h, T, geo);
+        BandUpload U = upload_band_chunked(h, T, img, dt, img_mem, W, C, geo, tile_first, tile_count);
+        const void* d_img = U.dev;
+        const long long row_lo = U.row_lo;
         StitchArgs S{H, W, th, tw, edge};
         const int B = net->maxB;
         T->tiles.reserve((size_t)B * C * th * tw * 4);
         T->sums.reserve((size_t)B * 16);
+        T->dbg_loop = 0.f;
+        Phase loop_phase(h, &T->dbg_loop);
         for (int64_t t0 = 0; t0 < tile_count; t0 += B) {
             const int nb = (int)std::min<int64_t>(B, tile_count - t0);
             const TileGeo* g = d_geo + tile_first + t0;
+            int need = 0;
+            for (int t = 0; t < nb; ++t) need = std::max(need, geo[tile_first + t0 + t].y1);
+            { Phase p(h, &Tm.ms_h2d); wait_rows(h, U, need); p.stop(); }     // stall (if any) on the overlapped upload
             { Phase p(h, &Tm.ms_prep); launch_tile_norm(h, d_img, dt, row_lo, (int)W, C, g, nb, th, tw, T->tiles.as<float>(), nullptr, T->sums.as<double>()); p.stop(); }
             { Phase p(h, &Tm.ms_conv); net->forward(T->tiles.as<float>(), nb); p.stop(); }
             NmsResult R;
@@ -551,9 +630,15 @@ y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dt, y3_mem img_m
             Tm.candidates += R.n_cand; Tm.kept += R.n_kept;
             { Phase p(h, &Tm.ms_stitch); T->stitch(P, R, g, S); p.stop(); }
         }
+        loop_phase.stop();
+        release_upload(h, U);
         { Phase p(h, &Tm.ms_d2h); deliver_preds(h, T, preds, preds_mem, cap, n_out); p.stop(); }
     }
     total.stop();
+    flush_phases(h);
+    if (getenv("Y3_DEBUG_TIMING"))
+        fprintf(stderr, "y3: total %.2f ms, batch loop %.2f ms, stage sum %.2f ms\n", Tm.ms_total, T->dbg_loop,
+                Tm.ms_h2d + Tm.ms_prep + Tm.ms_conv + Tm.ms_nms + Tm.ms_stitch + Tm.ms_d2h);
     Tm.kernels_launched = h->kernels_launched;
     Y3_API_END(h)
 }
@@ -576,6 +661,7 @@ y3_status y3_bench_forward(y3_handle h, int32_t batch, int32_t iters, float* ms_
     Phase p(h, &acc);
     for (int i = 0; i < iters; ++i) net->forward(h->stage_in.as<float>(), batch);
     p.stop();
+    flush_phases(h);
     *ms_per_iter = acc / iters;
     Y3_API_END(h)
 }

@@ -87,6 +87,11 @@ struct y3_context {
     y3::PostProc* post = nullptr;
     y3::Tiler* tiler = nullptr;
     y3::DevBuf stage_in, stage_out, stage_aux;   // host<->device staging for API calls
+    // stage timers: event pairs recorded on the stream, resolved once at the end of the API call
+    struct PhaseRec { cudaEvent_t a, b; float* dst; };
+    std::vector<PhaseRec> phase_log;
+    std::vector<cudaEvent_t> event_pool;
+    cudaStream_t copy_stream = nullptr;          // H2D of the image band, overlapped with compute
     y3::PinnedBuf pin_small;
 };
 

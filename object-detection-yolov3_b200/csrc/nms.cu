@@ -416,28 +416,23 @@ NmsResult PostProc::run(const CandSource& src, float iou_thr) {
             logit_floor = (float)(log(t2 / (1.0 - t2)) - 0.05);
         }
         const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
-        cudaEvent_t e0, e1;
-        Y3_CUDA(cudaEventCreate(&e0)); Y3_CUDA(cudaEventCreate(&e1));
-        Y3_CUDA(cudaEventRecord(e0, st));
+        if (!ev0) { Y3_CUDA(cudaEventCreate(&ev0)); Y3_CUDA(cudaEventCreate(&ev1)); }
+        Y3_CUDA(cudaEventRecord(ev0, st));
         if (total + 32 < (1ll << 32))
             k_candidates<uint32_t><<<blocks, 256, 0, st>>>(src, kl, total, logit_floor, keys[0].as<uint64_t>(), vals[0].as<uint32_t>(),
                                                            counters.as<unsigned long long>(), cap);
         else
             k_candidates<uint64_t><<<blocks, 256, 0, st>>>(src, kl, total, logit_floor, keys[0].as<uint64_t>(), vals[0].as<uint32_t>(),
                                                            counters.as<unsigned long long>(), cap);
-        Y3_CUDA(cudaEventRecord(e1, st));
+        Y3_CUDA(cudaEventRecord(ev1, st));
         Y3_LAUNCHED(ctx);
-        Y3_CUDA(cudaEventSynchronize(e1));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, e0, e1);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
-        last_cand_ms = ms;
     }
     unsigned long long* h_cnt = host_small.as<unsigned long long>();
     Y3_CUDA(cudaMemcpyAsync(h_cnt, counters.p, 8, cudaMemcpyDeviceToHost, st));
     Y3_CUDA(cudaStreamSynchronize(st));
     const int64_t K = (int64_t)h_cnt[0];
     R.n_cand = K;
+    { float ms = 0.f; if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) last_cand_ms = ms; }
     Y3_CHECK(K <= cap, Y3_ERR_NOSPACE, "candidate list overflow: %lld candidates, capacity %lld "
              "(raise y3_config.max_candidates)", (long long)K, (long long)cap);
     if (K == 0) return R;
@@ -464,7 +459,7 @@ NmsResult PostProc::run(const CandSource& src, float iou_thr) {
     // segment sizes are needed on the host only to route very large segments
     int64_t* h_off = reinterpret_cast<int64_t*>(host_small.as<unsigned char>() + 64);
     bool any_big = false, any_small = false;
-    if (K > BIG_SEGMENT) {
+    if (K > BIG_SEGMENT && src.rows_per_image > BIG_SEGMENT) {      // a segment never exceeds rows_per_image
         Y3_CUDA(cudaMemcpyAsync(h_off, seg_off.p, (size_t)(nseg + 1) * 8, cudaMemcpyDeviceToHost, st));
         Y3_CUDA(cudaStreamSynchronize(st));
         for (int s = 0; s < nseg; ++s) {

@@ -38,6 +38,7 @@ struct PostProc {
     DevBuf keys[2], vals[2], sort_tmp, sbox, sarea, supp, keepf, seg_off, counters, blk, kbuf;
     DevBuf o_box, o_score, o_label, o_img, o_src, o_rank;
     PinnedBuf host_small;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_cand_ms = 0.f;    // device time of the last k_candidates launch (decode+threshold+compaction)
     explicit PostProc(y3_context* c) : ctx(c) {}
     NmsResult run(const CandSource& src, float iou_thr);

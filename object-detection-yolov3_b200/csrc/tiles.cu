@@ -77,33 +77,32 @@ __device__ __forceinline__ double block_sum(double v, double* s_red) {
 
 static constexpr int TILE_SPLIT = 16;      // CTAs per tile (one CTA per tile left 116 of 148 SMs idle)
 
-__device__ __forceinline__ float tile_fetch(const void* __restrict__ img, int dtype, long long row_lo, int W, int C,
-                                            const TileGeo& g, int th, int tw, int e) {
-    // element e -> (c, ty, tx) with tx fastest (coalesced NCHW writes)
-    const int tx = e % tw;
-    const int r = e / tw;
-    const int ty = r % th;
-    const int c = r / th;
-    const int sy = g.y0 + reflect_idx(ty - g.pre_y, g.y1 - g.y0);
-    const int sx = g.x0 + reflect_idx(tx - g.pre_x, g.x1 - g.x0);
-    return load_any(img, dtype, ((long long)(sy - row_lo) * W + sx) * C + c);
+// source column of tile column tx (np.pad 'reflect' only at the borders; the interior is a plain offset)
+__device__ __forceinline__ int tile_src(int t, int pre, int n, int origin) {
+    const int q = t - pre;
+    return origin + (((unsigned)q < (unsigned)n) ? q : reflect_idx(q, n));
 }
 
 // pass 1: per-tile sum(x - s) and sum((x - s)^2) in fp64, s = the tile's first element (a shift that
 // removes the cancellation of the one-pass variance; for integer images every partial sum is an exact
 // integer < 2^53, so the result does not depend on the order of the atomics).
+// Rows of the (c, ty) plane are strided over the CTAs of a tile, threads run along tx (coalesced).
 __global__ void __launch_bounds__(512)
 k_tile_stats(const void* __restrict__ img, int dtype, long long row_lo, int W, int C, const TileGeo* __restrict__ geo,
              int th, int tw, double* __restrict__ sums /*[count][2]*/) {
     __shared__ double s_red[33];
     const TileGeo g = geo[blockIdx.y];
-    const int n_el = th * tw * C;
-    const double shift = (double)tile_fetch(img, dtype, row_lo, W, C, g, th, tw, 0);
+    const int ny = g.y1 - g.y0, nx = g.x1 - g.x0;
+    const double shift = (double)load_any(img, dtype, ((long long)(tile_src(0, g.pre_y, ny, g.y0) - row_lo) * W + tile_src(0, g.pre_x, nx, g.x0)) * C);
     double a1 = 0.0, a2 = 0.0;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += gridDim.x * blockDim.x) {
-        const double d = (double)tile_fetch(img, dtype, row_lo, W, C, g, th, tw, e) - shift;
-        a1 += d;
-        a2 += d * d;
+    for (int r = blockIdx.x; r < C * th; r += gridDim.x) {
+        const int c = r / th, ty = r - c * th;
+        const long long rowbase = (long long)(tile_src(ty, g.pre_y, ny, g.y0) - row_lo) * W;
+        for (int tx = threadIdx.x; tx < tw; tx += blockDim.x) {
+            const double d = (double)load_any(img, dtype, (rowbase + tile_src(tx, g.pre_x, nx, g.x0)) * C + c) - shift;
+            a1 += d;
+            a2 += d * d;
+        }
     }
     a1 = block_sum(a1, s_red);
     a2 = block_sum(a2, s_red);
@@ -118,8 +117,9 @@ __global__ void __launch_bounds__(512)
 k_tile_write(const void* __restrict__ img, int dtype, long long row_lo, int W, int C, const TileGeo* __restrict__ geo,
              int th, int tw, const double* __restrict__ sums, float* __restrict__ out, float* __restrict__ stats) {
     const TileGeo g = geo[blockIdx.y];
+    const int ny = g.y1 - g.y0, nx = g.x1 - g.x0;
     const int n_el = th * tw * C;
-    const double shift = (double)tile_fetch(img, dtype, row_lo, W, C, g, th, tw, 0);
+    const double shift = (double)load_any(img, dtype, ((long long)(tile_src(0, g.pre_y, ny, g.y0) - row_lo) * W + tile_src(0, g.pre_x, nx, g.x0)) * C);
     const double m1 = sums[2 * blockIdx.y] / (double)n_el;
     double var = sums[2 * blockIdx.y + 1] / (double)n_el - m1 * m1;
     if (var < 0.0) var = 0.0;
@@ -127,9 +127,14 @@ k_tile_write(const void* __restrict__ img, int dtype, long long row_lo, int W, i
     const float sd = (float)sqrt(var);
     float* o = out + (long long)blockIdx.y * n_el;
     const bool center_only = sd <= 1.0f;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_el; e += gridDim.x * blockDim.x) {
-        const float d = __fsub_rn(tile_fetch(img, dtype, row_lo, W, C, g, th, tw, e), mu);
-        o[e] = center_only ? d : __fdiv_rn(d, sd);
+    for (int r = blockIdx.x; r < C * th; r += gridDim.x) {
+        const int c = r / th, ty = r - c * th;
+        const long long rowbase = (long long)(tile_src(ty, g.pre_y, ny, g.y0) - row_lo) * W;
+        float* orow = o + (long long)r * tw;
+        for (int tx = threadIdx.x; tx < tw; tx += blockDim.x) {
+            const float d = __fsub_rn(load_any(img, dtype, (rowbase + tile_src(tx, g.pre_x, nx, g.x0)) * C + c), mu);
+            orow[tx] = center_only ? d : __fdiv_rn(d, sd);
+        }
     }
     if (stats && blockIdx.x == 0 && threadIdx.x == 0) { stats[2 * blockIdx.y] = mu; stats[2 * blockIdx.y + 1] = sd; }
 }
@@ -139,9 +144,10 @@ void launch_tile_norm(y3_context* ctx, const void* img_dev, int dtype, long long
     if (count <= 0) return;
     Y3_CUDA(cudaMemsetAsync(sums_scratch, 0, (size_t)count * 16, ctx->stream));
     dim3 grid(TILE_SPLIT, count);
-    k_tile_stats<<<grid, 512, 0, ctx->stream>>>(img_dev, dtype, row_lo, W, C, geo_dev, th, tw, sums_scratch);
+    const int threads = tw >= 512 ? 512 : (tw >= 256 ? 256 : 128);
+    k_tile_stats<<<grid, threads, 0, ctx->stream>>>(img_dev, dtype, row_lo, W, C, geo_dev, th, tw, sums_scratch);
     Y3_LAUNCHED(ctx);
-    k_tile_write<<<grid, 512, 0, ctx->stream>>>(img_dev, dtype, row_lo, W, C, geo_dev, th, tw, sums_scratch, out, stats);
+    k_tile_write<<<grid, threads, 0, ctx->stream>>>(img_dev, dtype, row_lo, W, C, geo_dev, th, tw, sums_scratch, out, stats);
     Y3_LAUNCHED(ctx);
 }
 

@@ -28,6 +28,7 @@ struct Tiler {
     y3_context* ctx;
     DevBuf geo, img, tiles, ibox, flags, acc, dets, sums;
     int64_t acc_rows = 0;
+    float dbg_loop = 0.f;
     explicit Tiler(y3_context* c) : ctx(c) {}
     // appends the surviving boxes of R (image index = tile index inside geo_dev) to acc; returns how many
     int64_t stitch(PostProc* post, const NmsResult& R, const TileGeo* geo_dev, const StitchArgs& S);
