@@ -452,51 +452,52 @@ const void* upload_band(y3_context* h, Tiler* T, const void* img, y3_dtype dt, y
     return T->img.p;
 }
 
-// Same, but the copy is issued in row chunks on a separate stream with one event per chunk, so that the
-// first tile batches start while later rows are still in flight (pinned host memory overlaps fully).
+// Same band, but uploaded just in time: the rows batch k+1 needs are copied on a separate stream while
+// batch k computes (pinned host memory overlaps fully).  Small per-batch copies never hog a copy engine,
+// so stream-ordered work of the compute stream is not queued behind a long transfer.
 struct BandUpload {
-    const void* dev = nullptr;
+    const void* dev = nullptr;      // device address of image row `row_lo`
+    const char* host = nullptr;
     long long row_lo = 0;
-    int chunk_rows = 0;
-    std::vector<cudaEvent_t> done;     // done[k]: rows [row_lo, row_lo + (k+1)*chunk_rows) are resident
+    int hi = 0, next_row = 0;       // rows [row_lo, next_row) have been enqueued
+    size_t row_bytes = 0;
+    std::vector<cudaEvent_t> ev;    // events to return to the pool
 };
-BandUpload upload_band_chunked(y3_context* h, Tiler* T, const void* img, y3_dtype dt, y3_mem mem, int64_t W, int C,
-                               const std::vector<TileGeo>& geo, int64_t first, int64_t count) {
+BandUpload begin_band_upload(y3_context* h, Tiler* T, const void* img, y3_dtype dt, y3_mem mem, int64_t W, int C,
+                             const std::vector<TileGeo>& geo, int64_t first, int64_t count) {
     BandUpload U;
     if (mem == Y3_MEM_DEVICE) { U.dev = img; return U; }
     int lo = geo[first].y0, hi = geo[first].y1;
     for (int64_t t = first; t < first + count; ++t) { lo = std::min(lo, geo[t].y0); hi = std::max(hi, geo[t].y1); }
-    const size_t row_bytes = (size_t)W * C * dtype_size(dt);
-    T->img.reserve((size_t)(hi - lo) * row_bytes);
+    U.row_bytes = (size_t)W * C * dtype_size(dt);
+    T->img.reserve((size_t)(hi - lo) * U.row_bytes);
     if (!h->copy_stream) Y3_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    U.dev = T->img.p; U.row_lo = lo;
-    U.chunk_rows = (int)std::max<size_t>(64, ((size_t)32 << 20) / row_bytes);     // ~32 MB per chunk
-    // the previous call's kernels may still read T->img: order the copies after the compute stream
+    U.dev = T->img.p; U.host = static_cast<const char*>(img); U.row_lo = lo; U.hi = hi; U.next_row = lo;
+    // kernels of the previous call may still read T->img: order the first copy after the compute stream
     cudaEvent_t gate = take_event(h);
     Y3_CUDA(cudaEventRecord(gate, h->stream));
     Y3_CUDA(cudaStreamWaitEvent(h->copy_stream, gate, 0));
-    h->event_pool.push_back(gate);
-    for (int r = lo; r < hi; r += U.chunk_rows) {
-        const int n = std::min(U.chunk_rows, hi - r);
-        Y3_CUDA(cudaMemcpyAsync(static_cast<char*>(T->img.p) + (size_t)(r - lo) * row_bytes,
-                                static_cast<const char*>(img) + (size_t)r * row_bytes, (size_t)n * row_bytes,
-                                cudaMemcpyHostToDevice, h->copy_stream));
-        cudaEvent_t e = take_event(h);
-        Y3_CUDA(cudaEventRecord(e, h->copy_stream));
-        U.done.push_back(e);
-    }
+    U.ev.push_back(gate);
     return U;
 }
-// make the compute stream wait until image rows < row_end are resident
-void wait_rows(y3_context* h, const BandUpload& U, int row_end) {
-    if (U.done.empty()) return;
-    int k = (int)((row_end - U.row_lo + U.chunk_rows - 1) / U.chunk_rows) - 1;
-    k = std::max(0, std::min(k, (int)U.done.size() - 1));
-    Y3_CUDA(cudaStreamWaitEvent(h->stream, U.done[k], 0));
+// enqueue (copy stream) the rows up to row_end that are not on their way yet; returns the event to wait on
+cudaEvent_t upload_rows_until(y3_context* h, BandUpload& U, int row_end) {
+    if (!U.host) return nullptr;
+    row_end = std::min(row_end, U.hi);
+    if (row_end > U.next_row) {
+        Y3_CUDA(cudaMemcpyAsync(const_cast<char*>(static_cast<const char*>(U.dev)) + (size_t)(U.next_row - U.row_lo) * U.row_bytes,
+                                U.host + (size_t)U.next_row * U.row_bytes, (size_t)(row_end - U.next_row) * U.row_bytes,
+                                cudaMemcpyHostToDevice, h->copy_stream));
+        U.next_row = row_end;
+    }
+    cudaEvent_t e = take_event(h);
+    Y3_CUDA(cudaEventRecord(e, h->copy_stream));
+    U.ev.push_back(e);
+    return e;
 }
 void release_upload(y3_context* h, BandUpload& U) {
-    for (cudaEvent_t e : U.done) h->event_pool.push_back(e);
-    U.done.clear();
+    for (cudaEvent_t e : U.ev) h->event_pool.push_back(e);
+    U.ev.clear();
 }
 const TileGeo* upload_geo(y3_context* h, Tiler* T, const std::vector<TileGeo>& geo) {
     T->geo.reserve(geo.size() * sizeof(TileGeo));
@@ -606,9 +607,16 @@ y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dt, y3_mem img_m
     *n_out = 0;
     if (tile_count > 0) {
         const TileGeo* d_geo = upload_geo(h, T, geo);
-        BandUpload U = upload_band_chunked(h, T, img, dt, img_mem, W, C, geo, tile_first, tile_count);
+        BandUpload U = begin_band_upload(h, T, img, dt, img_mem, W, C, geo, tile_first, tile_count);
         const void* d_img = U.dev;
         const long long row_lo = U.row_lo;
+        auto rows_needed = [&](int64_t t0) {                  // last image row (exclusive) batch t0 reads
+            int need = 0;
+            const int64_t n = std::min<int64_t>(net->maxB, tile_count - t0);
+            for (int64_t t = 0; t < n; ++t) need = std::max(need, geo[tile_first + t0 + t].y1);
+            return need;
+        };
+        cudaEvent_t ready = upload_rows_until(h, U, rows_needed(0));
         StitchArgs S{H, W, th, tw, edge};
         const int B = net->maxB;
         T->tiles.reserve((size_t)B * C * th * tw * 4);
@@ -618,9 +626,12 @@ y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dt, y3_mem img_m
         for (int64_t t0 = 0; t0 < tile_count; t0 += B) {
             const int nb = (int)std::min<int64_t>(B, tile_count - t0);
             const TileGeo* g = d_geo + tile_first + t0;
-            int need = 0;
-            for (int t = 0; t < nb; ++t) need = std::max(need, geo[tile_first + t0 + t].y1);
-            { Phase p(h, &Tm.ms_h2d); wait_rows(h, U, need); p.stop(); }     // stall (if any) on the overlapped upload
+            {   // wait for this batch's rows, then start the next batch's upload so it overlaps this batch's compute
+                Phase p(h, &Tm.ms_h2d);
+                if (ready) Y3_CUDA(cudaStreamWaitEvent(h->stream, ready, 0));
+                p.stop();
+                if (t0 + B < tile_count) ready = upload_rows_until(h, U, rows_needed(t0 + B));
+            }
             { Phase p(h, &Tm.ms_prep); launch_tile_norm(h, d_img, dt, row_lo, (int)W, C, g, nb, th, tw, T->tiles.as<float>(), nullptr, T->sums.as<double>()); p.stop(); }
             { Phase p(h, &Tm.ms_conv); net->forward(T->tiles.as<float>(), nb); p.stop(); }
             NmsResult R;
