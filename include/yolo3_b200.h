@@ -216,6 +216,11 @@ y3_status y3_debug_layer_output(y3_handle h, const char* layer, int32_t batch, f
  * base_offset (addr >> 7) & 7; entry (v, i) should equal rows shifts[i] .. shifts[i]+127 of a. */
 y3_status y3_debug_umma_rowshift(y3_handle h, const uint16_t* a_bf16, const int32_t* shifts, int32_t n_shift, float* out);
 
+/* Hardware probe (test hook): im2col-mode TMA loads of 128 output pixels x 64 channels.  x_bf16 NHWC bf16 bits;
+ * probes [n][6] = c, w, h, n, tap_w, tap_h; out [n][128][64] = the raw (128B-swizzled) shared-memory tiles. */
+y3_status y3_debug_im2col(y3_handle h, const uint16_t* x_bf16, int32_t N, int32_t H, int32_t W, int32_t C, int32_t stride,
+                          int32_t pad_lo, int32_t pad_hi, int32_t ksize, const int32_t* probes, int32_t n_probe, uint16_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,6 +128,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 const int x0 = (r - ty * P.tiles_x) * P.BW;
                 const int y0 = ty * P.BH;
                 const int n0 = nt * BN;
+                int im_w = 0, im_h = 0, im_n = 0;
+                if (P.im2col) {                               // x0 = first flattened output pixel of this tile
+                    const int per = P.im_ho * P.im_wo;
+                    im_n = x0 / per;
+                    const int rem = x0 - im_n * per;
+                    const int oh_ = rem / P.im_wo;
+                    im_h = oh_ * P.im_stride + P.im_lower;
+                    im_w = (rem - oh_ * P.im_wo) * P.im_stride + P.im_lower;
+                }
                 const int p = it & 1;
                 const uint32_t use = (uint32_t)(it >> 1);
                 if (P.has_res) {
@@ -144,7 +153,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                         mbar_wait(&empty[stage], phase ^ 1u);
                         unsigned char* sa = stage_base + stage * C::STAGE_BYTES;
                         mbar_expect_tx(&full[stage], (uint32_t)(rows * BK * 2 + C::B_BYTES));
-                        if (P.stride == 1) {
+                        if (P.im2col) {
+                            tma_load_im2col_4d(sa, &map_a, &full[stage], kc * BK, im_w, im_h, im_n, (uint16_t)kw, (uint16_t)kh);
+                        } else if (P.stride == 1) {
                             if (kc < P.k_split) tma_load_4d(sa, &map_a, &full[stage], kc * BK, x0 + kw - P.pad, y0 + kh - P.pad, img);
                             else tma_load_4d(sa, &map_a2, &full[stage], (kc - P.k_split) * BK, x0 + kw - P.pad, y0 + kh - P.pad, img);
                         }
@@ -335,6 +346,43 @@ void encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64
              (unsigned long long)(rank > 4 ? gdim[4] : 0), bdim[0], rank > 1 ? bdim[1] : 0, rank > 2 ? bdim[2] : 0,
              rank > 3 ? bdim[3] : 0, rank > 4 ? bdim[4] : 0, (unsigned long long)(rank > 1 ? gstr[0] : 0),
              swizzle_bytes, base);
+}
+
+
+typedef CUresult (*PFN_encodeIm2col_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+void encode_tmap_im2col_bf16(CUtensorMap* map, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
+                             const int* lower, const int* upper, uint32_t channels, uint32_t pixels, uint32_t stride,
+                             int swizzle_bytes) {
+    static PFN_encodeIm2col_t fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        Y3_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q));
+        Y3_CHECK(p && q == cudaDriverEntryPointSuccess, Y3_ERR_CUDA, "cuTensorMapEncodeIm2col not available");
+        fn = reinterpret_cast<PFN_encodeIm2col_t>(p);
+    }
+    cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+    cuuint64_t gstr[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+    cuuint32_t estr[4] = {1, stride, stride, 1};
+    int lo[2] = {lower[0], lower[1]}, up[2] = {upper[0], upper[1]};
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, lo, up, channels, pixels,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    int drv = 0;
+    if (r == CUDA_SUCCESS && cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010) {
+        // same workaround CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp) for tensors below 128 KB
+        const uint64_t bytes = (dims[3] - 1) * strides_bytes[2] + (dims[2] - 1) * strides_bytes[1] + (dims[1] - 1) * strides_bytes[0] + dims[0] * 2;
+        if (bytes < 131072) reinterpret_cast<uint64_t*>(map)[1] &= ~(1llu << 21);
+    }
+    Y3_CHECK(r == CUDA_SUCCESS, Y3_ERR_CUDA,
+             "cuTensorMapEncodeIm2col failed (%d): dims [%llu,%llu,%llu,%llu] lower [%d,%d] upper [%d,%d] ch %u px %u stride %u",
+             (int)r, (unsigned long long)gdim[0], (unsigned long long)gdim[1], (unsigned long long)gdim[2],
+             (unsigned long long)gdim[3], lo[0], lo[1], up[0], up[1], channels, pixels, stride);
 }
 
 template <int BN, int BK>

@@ -15,6 +15,9 @@ struct ConvArgs {
     int stride, pad;         // 1|2 ; left/top zero padding (TF SAME: s1 k3 -> 1, s2 -> 0)
     int a_cpitch;            // channel pitch of the input buffer (phase offset of the stride-2 view)
     int k_split;             // K chunks [0,k_split) come from map_a, the rest from map_a2 (fused upsample+concat)
+    int im2col;              // A operand through an im2col-mode tensor map: M tile = 128 consecutive output pixels
+    int im_ho, im_wo;        //   output grid of one image
+    int im_stride, im_lower; //   traversal stride and lower pixel-box corner (= -pad_before)
     int has_res, linear, out_f32;
     int Ho, Wo;
     const float* bias;       // [cout_pad]
@@ -41,3 +44,11 @@ void launch_conv(y3_context* ctx, const ConvLaunch& L);
 void launch_conv2(y3_context* ctx, const ConvLaunch& L);
 
 }  // namespace y3
+
+namespace y3 {
+// im2col-mode tensor map over an NHWC bf16 tensor: dims (C, W, H, N); lower/upper = pixel-box corners (W, H);
+// pixels = output pixels per load (M tile), channels = K chunk; stride = traversal stride (W, H).
+void encode_tmap_im2col_bf16(CUtensorMap* map, const void* base, const uint64_t* dims /*4*/, const uint64_t* strides_bytes /*3*/,
+                             const int* lower /*2*/, const int* upper /*2*/, uint32_t channels, uint32_t pixels, uint32_t stride,
+                             int swizzle_bytes);
+}

@@ -119,6 +119,15 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                 const int x0 = (r - ty * P.tiles_x) * P.BW;
                 const int y0 = ty * P.BH;
                 const int n0 = nt * BN2;
+                int im_w = 0, im_h = 0, im_n = 0;
+                if (P.im2col) {                               // x0 = first flattened output pixel of this tile
+                    const int per = P.im_ho * P.im_wo;
+                    im_n = x0 / per;
+                    const int rem = x0 - im_n * per;
+                    const int oh_ = rem / P.im_wo;
+                    im_h = oh_ * P.im_stride + P.im_lower;
+                    im_w = (rem - oh_ * P.im_wo) * P.im_stride + P.im_lower;
+                }
                 const int p = (C::NSTG == 2) ? (it & 1) : 0;
                 const uint32_t use = (C::NSTG == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
                 if (P.has_res) {
@@ -136,7 +145,9 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                         unsigned char* sa = stage_base + stage * C::STAGE_BYTES;
                         const uint32_t lead_full = mapa_u32(&full[stage], 0);
                         if (rank == 0) mbar_expect_tx(&full[stage], (uint32_t)(2 * (rows * BK * 2 + C::B_BYTES)));
-                        if (P.stride == 1) {
+                        if (P.im2col) {
+                            tma2_load_im2col_4d(sa, &map_a, lead_full, kc * BK, im_w, im_h, im_n, (uint16_t)kw, (uint16_t)kh);
+                        } else if (P.stride == 1) {
                             if (kc < P.k_split) tma2_load_4d(sa, &map_a, lead_full, kc * BK, x0 + kw - P.pad, y0 + kh - P.pad, img);
                             else tma2_load_4d(sa, &map_a2, lead_full, (kc - P.k_split) * BK, x0 + kw - P.pad, y0 + kh - P.pad, img);
                         }

@@ -302,10 +302,23 @@ void Net::make_launches(Op& op) {
         A.bias = op.bias.as<float>(); A.scale = op.scale.as<float>(); A.shift = op.shift.as<float>();
         A.cout_valid = op.cout;
         A.n_tiles_n = op.cout_pad / bn;
-        op.flat = flat;
+        op.flat = flat;     // (im2col ops set it to true below)
 
         // ---- A operand
-        if (flat) {
+        static const bool use_im2col = getenv("Y3_NO_IM2COL") == nullptr;
+        if (op.k == 3 && !phased && use_im2col) {
+            // im2col-mode TMA: an M tile is 128 consecutive output pixels of the flattened (n, ho, wo) axis,
+            // padding (TF SAME: s1 (1,1); s2 (0 before, 1 after)) and the traversal stride live in the map
+            const int ho = ti.h / op.stride, wo = ti.w / op.stride;
+            A.im2col = 1; A.im_ho = ho; A.im_wo = wo; A.im_stride = op.stride; A.im_lower = op.stride == 1 ? -1 : 0;
+            A.BH = 1; A.BW = 128; A.Ho = 1;
+            op.flat = true; op.pix_per_img = ho * wo;
+            uint64_t dims[4] = {(uint64_t)cin, (uint64_t)ti.w, (uint64_t)ti.h, (uint64_t)maxB};
+            uint64_t str[3] = {(uint64_t)pitch_in * 2, (uint64_t)ti.w * pitch_in * 2, (uint64_t)ti.h * ti.w * pitch_in * 2};
+            int lower[2] = {A.im_lower, A.im_lower};
+            int upper[2] = {1 - 2, 1 - 2};                      // pad_after (1) - (k-1) for both strides
+            encode_tmap_im2col_bf16(&L.map_a, in_base, dims, str, lower, upper, (uint32_t)bk, 128, (uint32_t)op.stride, bk * 2);
+        } else if (flat) {
             const uint64_t M = (uint64_t)maxB * ti.h * ti.w;
             A.BH = 1; A.BW = 128; A.Ho = 1; op.pix_per_img = ti.h * ti.w;
             uint64_t dims[4] = {(uint64_t)cin, M, 1, 1};
@@ -363,7 +376,7 @@ void Net::make_launches(Op& op) {
             const TensorInfo& to = tensors[op.out.t];
             __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(to.ptr) + op.out.coff;
             const int po = to.c;
-            if (flat) {
+            if (flat || A.im2col) {
                 const uint64_t M = (uint64_t)maxB * to.h * to.w;
                 uint64_t dims[4] = {(uint64_t)op.cout, M, 1, 1};
                 uint64_t str[3] = {(uint64_t)po * 2, M * po * 2, M * po * 2};
@@ -384,7 +397,15 @@ void Net::make_launches(Op& op) {
                 uint32_t box[4] = {(uint32_t)oc, (uint32_t)A.BW, (uint32_t)A.BH, 1};
                 encode_tmap_bf16(&L.map_out, obase, 4, dims, str, box, oc * 2);
             }
-            if (A.has_res) {
+            if (A.has_res && A.im2col) {
+                const TensorInfo& tr = tensors[op.res.t];
+                const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(tr.ptr) + op.res.coff;
+                const uint64_t M = (uint64_t)maxB * tr.h * tr.w;
+                uint64_t dims[4] = {(uint64_t)op.res.c, M, 1, 1};
+                uint64_t str[3] = {(uint64_t)tr.c * 2, M * tr.c * 2, M * tr.c * 2};
+                uint32_t box[4] = {(uint32_t)oc, 128, 1, 1};
+                encode_tmap_bf16(&L.map_res, rbase, 4, dims, str, box, oc * 2);
+            } else if (A.has_res) {
                 const TensorInfo& tr = tensors[op.res.t];
                 const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(tr.ptr) + op.res.coff;
                 uint64_t dims[4] = {(uint64_t)op.res.c, (uint64_t)tr.w, (uint64_t)tr.h, (uint64_t)maxB};

@@ -249,3 +249,26 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t mask) {
 }
 
 }}  // namespace y3::ptx
+
+// ======================================================================= im2col-mode TMA loads
+namespace y3 { namespace ptx {
+// 128 consecutive OUTPUT pixels (flattened n,h,w; traversal stride and padding live in the tensor map) x one
+// K chunk of channels, for filter tap (ow, oh).  (c, w, h, n) = channel chunk and the INPUT coordinate of the
+// first pixel's window origin (w = wo*stride + lower_corner_w ...).
+__device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c, int w, int h, int n,
+                                                   uint16_t ow, uint16_t oh) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2], {%7, %8};\n" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(ow), "h"(oh)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col_4d(void* dst, const CUtensorMap* m, uint32_t bar, int c, int w, int h, int n,
+                                                    uint16_t ow, uint16_t oh) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+        "%5, %6}], [%2], {%7, %8};\n" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(ow), "h"(oh)
+        : "memory");
+}
+}}  // namespace y3::ptx

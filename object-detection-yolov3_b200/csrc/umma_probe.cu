@@ -101,3 +101,63 @@ extern "C" y3_status y3_debug_umma_rowshift(y3_handle h, const uint16_t* a_bf16 
         return e.code;
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Probe 2: im2col-mode TMA.  One load of 128 output pixels x 64 channels for tap (ow, oh) starting at
+// input coordinate (w, h, n); the raw (swizzled) 16 KB tile is copied out for comparison on the host.
+namespace y3 {
+struct Im2colProbe { int c, w, h, n, ow, oh; };
+__global__ void __launch_bounds__(128, 1)
+k_im2col_probe(const __grid_constant__ CUtensorMap map, Im2colProbe P, uint4* __restrict__ out /*[1024] 16-B pieces*/) {
+#if defined(__CUDA_ARCH_FEAT_SM100_ALL) || defined(__CUDA_ARCH_FEAT_SM101_ALL)
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16384);
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u);
+    if (threadIdx.x == 0) { ptx::mbar_init(bar, 1); ptx::fence_mbar_init(); }
+    ptx::fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ptx::mbar_expect_tx(bar, 16384);
+        ptx::tma_load_im2col_4d(smem, &map, bar, P.c, P.w, P.h, P.n, (uint16_t)P.ow, (uint16_t)P.oh);
+    }
+    ptx::mbar_wait(bar, 0);
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) out[i] = reinterpret_cast<uint4*>(smem)[i];
+#endif
+}
+}  // namespace y3
+
+extern "C" y3_status y3_debug_im2col(y3_handle h, const uint16_t* x_bf16 /*NHWC*/, int32_t N, int32_t H, int32_t W, int32_t C,
+                                     int32_t stride, int32_t pad_lo, int32_t pad_hi, int32_t ksize, const int32_t* probes /*[n][6]*/,
+                                     int32_t n_probe, uint16_t* out /*[n][128][64] raw smem*/) {
+    using namespace y3;
+    if (!h || !x_bf16 || !probes || !out) return Y3_ERR_INVALID;
+    try {
+        Y3_CUDA(cudaSetDevice(h->device));
+        DevBuf dX, dO;
+        const size_t nx = (size_t)N * H * W * C;
+        dX.reserve(nx * 2 + 131072); dO.reserve(16384);
+        Y3_CUDA(cudaMemset(dX.p, 0, nx * 2 + 131072));
+        Y3_CUDA(cudaMemcpy(dX.p, x_bf16, nx * 2, cudaMemcpyHostToDevice));
+        CUtensorMap m;
+        uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+        int lower[2] = {-pad_lo, -pad_lo};
+        int upper[2] = {pad_hi - (ksize - 1), pad_hi - (ksize - 1)};
+        encode_tmap_im2col_bf16(&m, dX.p, dims, str, lower, upper, 64, 128, (uint32_t)stride, 128);
+        const int smem = 1024 + 16384 + 64;
+        Y3_CUDA(cudaFuncSetAttribute(k_im2col_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        for (int i = 0; i < n_probe; ++i) {
+            Im2colProbe P{probes[6 * i], probes[6 * i + 1], probes[6 * i + 2], probes[6 * i + 3], probes[6 * i + 4], probes[6 * i + 5]};
+            k_im2col_probe<<<1, 128, smem, h->stream>>>(m, P, dO.as<uint4>());
+            Y3_CUDA(cudaGetLastError());
+            Y3_CUDA(cudaStreamSynchronize(h->stream));
+            Y3_CUDA(cudaMemcpy(out + (size_t)i * 8192, dO.p, 16384, cudaMemcpyDeviceToHost));
+        }
+        return Y3_OK;
+    } catch (const Error& e) {
+        h->last_error = e.msg;
+        cudaGetLastError();
+        return e.code;
+    }
+}

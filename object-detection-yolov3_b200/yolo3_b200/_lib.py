@@ -62,6 +62,8 @@ PROTOTYPES = {
     "y3_bench_forward": (c_int32, [c_void_p, c_int32, c_int32, POINTER(c_float)]),
     "y3_profile_layers": (c_int32, [c_void_p, c_int32, c_int32, c_char_p, c_int64]),
     "y3_debug_umma_rowshift": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "y3_debug_im2col": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                  c_void_p, c_int32, c_void_p]),
     "y3_debug_layer_output": (c_int32, [c_void_p, c_char_p, c_int32, c_void_p, c_int64, POINTER(c_int32)]),
 }
 
