@@ -54,7 +54,7 @@ def bench_weights(seed=0):
     return weights.random_init(1, NC, len(ANCHORS), seed=seed, randomize_bn=True)
 
 
-def calibrate_heads(eng, w, sample_tiles, target_std=1.0, pass_frac=0.005, nc=NC, n_anchors=len(ANCHORS)):
+def calibrate_heads(eng, w, sample_tiles, target_std=1.0, pass_frac=0.005, nc=NC, n_anchors=len(ANCHORS), interior=True):
     """Random-init heads are useless as a detection regime: the all-ones upsample inflates the three heads
     by 400x relative to each other and every output channel is a large constant plus a small spatial
     signal, so whole channels pass or fail the score threshold together.  Standardise every detection
@@ -67,7 +67,7 @@ def calibrate_heads(eng, w, sample_tiles, target_std=1.0, pass_frac=0.005, nc=NC
     for i, h in enumerate(heads):
         k = "feature_map_%d" % (i + 1)
         g = h.shape[2]
-        m = max(1, g // 4)                                  # interior cells only: the zero padding at tile
+        m = max(1, g // 4) if interior else 0               # interior cells only: the zero padding at tile
         core = h[:, :, m:g - m, m:g - m]                    # borders would otherwise dominate the statistics
         mu = core.mean(axis=(0, 2, 3)).astype(np.float64)
         sd = np.maximum(core.std(axis=(0, 2, 3)).astype(np.float64), 1e-12)
@@ -310,7 +310,7 @@ def main():
                 w2 = _wts.random_init(3, 80, 3, seed=0, randomize_bn=True)
                 e2.load_weights(w2)
                 x2 = np.random.default_rng(1).standard_normal((64, 3, 416, 416)).astype(np.float32)
-                calibrate_heads(e2, w2, x2[:4], pass_frac=0.002, nc=80)
+                calibrate_heads(e2, w2, x2[:8], pass_frac=0.002, nc=80, interior=False)
                 e2.detect(x2, MIN_BOX, IOU_THR, SCORE_THR)
                 e2.detect(x2, MIN_BOX, IOU_THR, SCORE_THR)
                 t2 = e2.timings()

@@ -12,7 +12,7 @@
 // Pipeline (all on ctx->stream):
 //   k_candidates      one thread per (row, class): threshold, ballot-compact, emit a 64-bit key
 //                     [segment | ~orderable(score) | row] and the global row as the value
-//   radix sort        cub::DeviceRadixSort on the used key bits only (toolkit primitive)
+//   k_rs_*            own stable LSD radix sort (8 bits / pass) on the used key bits only
 //   k_gather_sorted   boxes / areas of the sorted candidates as SoA (coalesced for the sweeps)
 //   k_seg_offsets     segment (= image x class) boundaries by binary search on the sorted keys
 //   k_nms_segments    one CTA per segment: per 512-box chunk a shared-memory IoU bitmask
@@ -24,7 +24,6 @@
 // The n x n/64 bitmask is never materialised in HBM.
 #include "postproc.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
 #include <math.h>
 
 namespace y3 {
@@ -159,6 +158,93 @@ __global__ void k_seg_offsets(const uint64_t* __restrict__ keys, int64_t n, int 
         if ((keys[mid] >> seg_shift) < (uint64_t)s) lo = mid + 1; else hi = mid;
     }
     off[s] = lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// Stable LSD radix sort of (u64 key, u32 value) pairs, 8 bits per pass, over the used key bits only.
+//   k_rs_hist     per-block digit histogram (shared-memory atomics) -> hist[digit][block]
+//   k_rs_scan     exclusive scan of the digit-major histogram (one block; it is 256 x nblocks ints)
+//   k_rs_scatter  each block re-reads its elements IN ORDER, 256 at a time: rank inside the warp with
+//                 __match_any_sync, prefix across the 8 warps per digit, running per-digit offsets
+static constexpr int RS_THREADS = 256;
+static constexpr int RS_ITEMS = 16;
+static constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_hist(const uint64_t* __restrict__ keys, int64_t n, int shift, int nblocks, int* __restrict__ hist) {
+    __shared__ int s_h[256];
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const int64_t i = base + r * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&s_h[(int)((keys[i] >> shift) & 0xff)], 1);
+    }
+    __syncthreads();
+    hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = s_h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(1024)
+k_rs_scan(int* __restrict__ a, int64_t n) {
+    __shared__ long long s_part[1024];
+    const int64_t per = (n + 1023) / 1024;
+    const int64_t b0 = (int64_t)threadIdx.x * per;
+    long long sum = 0;
+    for (int64_t i = 0; i < per; ++i) if (b0 + i < n) sum += a[b0 + i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const long long v = (threadIdx.x >= o) ? s_part[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    long long run = s_part[threadIdx.x] - sum;
+    for (int64_t i = 0; i < per; ++i)
+        if (b0 + i < n) { const int c = a[b0 + i]; a[b0 + i] = (int)run; run += c; }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_scatter(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
+             uint32_t* __restrict__ vout, int64_t n, int shift, int nblocks, const int* __restrict__ hist) {
+    __shared__ int s_run[256];                 // next output slot of each digit for this block
+    __shared__ int s_cnt[RS_THREADS / 32][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    s_run[threadIdx.x] = hist[(int64_t)threadIdx.x * nblocks + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < RS_THREADS / 32; ++w) s_cnt[w][threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const int64_t i = base + r * RS_THREADS + threadIdx.x;
+        const bool valid = i < n;
+        uint64_t key = 0;
+        uint32_t val = 0;
+        int d = 256 + lane;                    // invalid lanes: unique pseudo-digits so they match nobody
+        if (valid) { key = kin[i]; val = vin[i]; d = (int)((key >> shift) & 0xff); }
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank == 0) s_cnt[warp][d] = __popc(peers);
+        __syncthreads();
+        {   // thread t owns digit t: exclusive prefix over the warps (in order => stable), advance the run
+            const int t = threadIdx.x;
+            int run = s_run[t];
+#pragma unroll
+            for (int w = 0; w < RS_THREADS / 32; ++w) { const int c = s_cnt[w][t]; s_cnt[w][t] = run; run += c; }
+            s_run[t] = run;
+        }
+        __syncthreads();
+        if (valid) {
+            const int pos = s_cnt[warp][d] + rank;
+            kout[pos] = key;
+            vout[pos] = val;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) s_cnt[w][threadIdx.x] = 0;     // the prefix step overwrote every entry
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -437,16 +523,27 @@ NmsResult PostProc::run(const CandSource& src, float iou_thr) {
              "(raise y3_config.max_candidates)", (long long)K, (long long)cap);
     if (K == 0) return R;
 
-    // sort by (segment, score desc, row asc)
-    size_t tmp_bytes = 0;
-    Y3_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys[0].as<uint64_t>(), keys[1].as<uint64_t>(),
-                                            vals[0].as<uint32_t>(), vals[1].as<uint32_t>(), K, 0, kl.total_bits, st));
-    sort_tmp.reserve(tmp_bytes);
-    Y3_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp.p, tmp_bytes, keys[0].as<uint64_t>(), keys[1].as<uint64_t>(),
-                                            vals[0].as<uint32_t>(), vals[1].as<uint32_t>(), K, 0, kl.total_bits, st));
-    count_launch(ctx, 2 * ((kl.total_bits + 7) / 8) + 1);
-    const uint64_t* skeys = keys[1].as<uint64_t>();
-    const uint32_t* svals = vals[1].as<uint32_t>();
+    // sort by (segment, score desc, row asc): own stable LSD radix sort over the used key bits
+    Y3_CHECK(K < (1ll << 31), Y3_ERR_UNSUPPORTED, "too many candidates (%lld)", (long long)K);
+    int src_buf = 0;
+    {
+        const int nblocks = ceil_div(K, RS_TILE);
+        sort_tmp.reserve((size_t)256 * nblocks * 4);
+        for (int shift = 0; shift < kl.total_bits; shift += 8) {
+            const int dst_buf = src_buf ^ 1;
+            k_rs_hist<<<nblocks, RS_THREADS, 0, st>>>(keys[src_buf].as<uint64_t>(), K, shift, nblocks, sort_tmp.as<int>());
+            Y3_LAUNCHED(ctx);
+            k_rs_scan<<<1, 1024, 0, st>>>(sort_tmp.as<int>(), (int64_t)256 * nblocks);
+            Y3_LAUNCHED(ctx);
+            k_rs_scatter<<<nblocks, RS_THREADS, 0, st>>>(keys[src_buf].as<uint64_t>(), vals[src_buf].as<uint32_t>(),
+                                                        keys[dst_buf].as<uint64_t>(), vals[dst_buf].as<uint32_t>(), K, shift, nblocks,
+                                                        sort_tmp.as<int>());
+            Y3_LAUNCHED(ctx);
+            src_buf = dst_buf;
+        }
+    }
+    const uint64_t* skeys = keys[src_buf].as<uint64_t>();
+    const uint32_t* svals = vals[src_buf].as<uint32_t>();
 
     sbox.reserve(K * 16); sarea.reserve(K * 4); supp.reserve(K); keepf.reserve(K);
     seg_off.reserve((size_t)(nseg + 1) * 8);
