@@ -150,7 +150,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--image-side", type=int, default=20000)
     ap.add_argument("--edge", type=int, default=64, help="EDGE_EFFECT_RANGE; 64 = BASELINE wording, 96 = reference constant")
-    ap.add_argument("--batch", type=int, default=64, help="tiles per forward batch")
+    ap.add_argument("--batch", type=int, default=128, help="tiles per forward batch")
     ap.add_argument("--cpu-sample-tiles", type=int, default=96)
     args = ap.parse_args()
 

@@ -142,10 +142,10 @@ CandSource dets_source(const float* dets_dev, int64_t n_per_img, int n_img, int 
 }
 
 // fused: the candidates are thresholded straight from the raw heads of the last forward
-CandSource heads_source(const Net* net, int n_img, bool filter, float min_box, float score_thr) {
+CandSource heads_source(const Net* net, int n_img, bool filter, float min_box, float score_thr, int head_set = 0) {
     CandSource s;
     s.from_heads = true;
-    s.dec = net->decode_args(n_img);
+    s.dec = net->decode_args(n_img, head_set);
     s.rows_per_image = net->rows_per_image; s.n_images = n_img; s.nc = net->nc;
     s.filter_small = filter; s.min_size = min_box; s.score_thr = score_thr;
     return s;
@@ -214,6 +214,7 @@ void y3_destroy(y3_handle h) {
     for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
     for (auto& r : h->phase_log) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->post_stream) cudaStreamDestroy(h->post_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -623,9 +624,37 @@ y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dt, y3_mem img_m
         T->sums.reserve((size_t)B * 16);
         T->dbg_loop = 0.f;
         Phase loop_phase(h, &T->dbg_loop);
-        for (int64_t t0 = 0; t0 < tile_count; t0 += B) {
+        // Software pipeline over tile batches: the conv stack of batch k+1 is enqueued on the main stream
+        // BEFORE the post-processing of batch k (fused decode/threshold, sort, NMS, stitch - which contains
+        // host synchronisations) runs on a second stream, reading the other set of head buffers.
+        if (!h->post_stream) Y3_CUDA(cudaStreamCreateWithFlags(&h->post_stream, cudaStreamNonBlocking));
+        static const bool overlap_post = getenv("Y3_NO_POST_OVERLAP") == nullptr;
+        std::vector<cudaEvent_t> heads_ready;
+        auto run_post = [&](int64_t t0, int nb, int set, cudaEvent_t ready_ev) {
+            cudaStream_t main_stream = h->stream;
+            if (overlap_post) {
+                Y3_CUDA(cudaStreamWaitEvent(h->post_stream, ready_ev, 0));
+                h->stream = h->post_stream;                    // every helper enqueues on ctx->stream
+            }
+            try {
+                NmsResult R;
+                { Phase p(h, &Tm.ms_nms);
+                  R = P->run(heads_source(net, nb, true, min_box, score_thr, set), iou_thr);
+                  p.stop(); Tm.ms_decode += P->last_cand_ms; }
+                Tm.candidates += R.n_cand; Tm.kept += R.n_kept;
+                { Phase p(h, &Tm.ms_stitch); T->stitch(P, R, d_geo + tile_first + t0, S); p.stop(); }
+            } catch (...) {
+                h->stream = main_stream;
+                throw;
+            }
+            h->stream = main_stream;
+        };
+        int64_t prev_t0 = -1; int prev_nb = 0, prev_set = 0; cudaEvent_t prev_ev = nullptr;
+        int it = 0;
+        for (int64_t t0 = 0; t0 < tile_count; t0 += B, ++it) {
             const int nb = (int)std::min<int64_t>(B, tile_count - t0);
             const TileGeo* g = d_geo + tile_first + t0;
+            const int set = it & 1;
             {   // wait for this batch's rows, then start the next batch's upload so it overlaps this batch's compute
                 Phase p(h, &Tm.ms_h2d);
                 if (ready) Y3_CUDA(cudaStreamWaitEvent(h->stream, ready, 0));
@@ -633,14 +662,25 @@ y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dt, y3_mem img_m
                 if (t0 + B < tile_count) ready = upload_rows_until(h, U, rows_needed(t0 + B));
             }
             { Phase p(h, &Tm.ms_prep); launch_tile_norm(h, d_img, dt, row_lo, (int)W, C, g, nb, th, tw, T->tiles.as<float>(), nullptr, T->sums.as<double>()); p.stop(); }
-            { Phase p(h, &Tm.ms_conv); net->forward(T->tiles.as<float>(), nb); p.stop(); }
-            NmsResult R;
-            { Phase p(h, &Tm.ms_nms);
-              R = P->run(heads_source(net, nb, true, min_box, score_thr), iou_thr);
-              p.stop(); Tm.ms_decode += P->last_cand_ms; }
-            Tm.candidates += R.n_cand; Tm.kept += R.n_kept;
-            { Phase p(h, &Tm.ms_stitch); T->stitch(P, R, g, S); p.stop(); }
+            { Phase p(h, &Tm.ms_conv); net->forward(T->tiles.as<float>(), nb, set); p.stop(); }
+            cudaEvent_t ev = take_event(h);
+            Y3_CUDA(cudaEventRecord(ev, h->stream));
+            heads_ready.push_back(ev);
+            if (overlap_post) {
+                if (prev_t0 >= 0) run_post(prev_t0, prev_nb, prev_set, prev_ev);     // batch k-1 while batch k computes
+                prev_t0 = t0; prev_nb = nb; prev_set = set; prev_ev = ev;
+            } else {
+                run_post(t0, nb, set, ev);
+            }
         }
+        if (overlap_post && prev_t0 >= 0) run_post(prev_t0, prev_nb, prev_set, prev_ev);
+        if (overlap_post) {                                     // the accumulated boxes live on the post stream
+            cudaEvent_t done = take_event(h);
+            Y3_CUDA(cudaEventRecord(done, h->post_stream));
+            Y3_CUDA(cudaStreamWaitEvent(h->stream, done, 0));
+            heads_ready.push_back(done);
+        }
+        for (cudaEvent_t e : heads_ready) h->event_pool.push_back(e);
         loop_phase.stop();
         release_upload(h, U);
         { Phase p(h, &Tm.ms_d2h); deliver_preds(h, T, preds, preds_mem, cap, n_out); p.stop(); }

@@ -92,6 +92,7 @@ struct y3_context {
     std::vector<PhaseRec> phase_log;
     std::vector<cudaEvent_t> event_pool;
     cudaStream_t copy_stream = nullptr;          // H2D of the image band, overlapped with compute
+    cudaStream_t post_stream = nullptr;          // candidates / sort / NMS / stitch of batch k while conv of k+1 runs
     y3::PinnedBuf pin_small;
 };
 

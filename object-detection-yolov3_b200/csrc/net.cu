@@ -210,6 +210,8 @@ void Net::build() {
         const size_t bytes = (size_t)maxB * gh[s] * gw[s] * head_pitch * 4;
         Y3_CUDA(cudaMalloc((void**)&head[s], bytes));
         owned.push_back(head[s]);
+        Y3_CUDA(cudaMalloc((void**)&head_b[s], bytes));
+        owned.push_back(head_b[s]);
     }
 
     // --- parameters + launch descriptors
@@ -555,7 +557,7 @@ void Net::load(int n, const char* const* names, DLManagedTensor* const* tensors_
 }
 
 // ------------------------------------------------------------------------------------------ forward
-void Net::forward(const float* in_dev, int b) {
+void Net::forward(const float* in_dev, int b, int head_set) {
     Y3_CHECK(loaded, Y3_ERR_STATE, "weights not (completely) loaded - missing %s", missing.c_str());
     Y3_CHECK(b >= 1 && b <= maxB, Y3_ERR_INVALID, "batch %d outside 1..%d", b, maxB);
     for (Op& op : ops) {
@@ -565,16 +567,18 @@ void Net::forward(const float* in_dev, int b) {
             continue;
         }
         if (cur_batch != b) set_batch(op, b);
+        if (op.kind == Op::DET)
+            for (ConvLaunch& L : op.launches) L.args.out32 = head_set ? head_b[op.head] : head[op.head];
         for (const ConvLaunch& L : op.launches) launch_conv(ctx, L);
     }
     cur_batch = b;
 }
 
-DecodeArgs Net::decode_args(int b) const {
+DecodeArgs Net::decode_args(int b, int head_set) const {
     DecodeArgs D;
     memset(&D, 0, sizeof(D));
     for (int s = 0; s < 3; ++s) {
-        D.head[s] = head[s]; D.gh[s] = gh[s]; D.gw[s] = gw[s]; D.row_start[s] = row_start[s];
+        D.head[s] = head_set ? head_b[s] : head[s]; D.gh[s] = gh[s]; D.gw[s] = gw[s]; D.row_start[s] = row_start[s];
         // np.asarray(img_size[0:2], float32) // np.asarray(grid_size, float32)   (model.py:127)
         D.stride_h[s] = floorf((float)H / (float)gh[s]);
         D.stride_w[s] = floorf((float)W / (float)gw[s]);

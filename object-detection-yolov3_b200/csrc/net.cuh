@@ -56,7 +56,8 @@ struct Net {
     std::vector<TensorInfo> tensors;
     std::vector<Op> ops;
     std::vector<void*> owned;
-    float* head[3] = {nullptr, nullptr, nullptr};
+    float* head[3] = {nullptr, nullptr, nullptr};        // head set 0
+    float* head_b[3] = {nullptr, nullptr, nullptr};      // head set 1 (post-processing of batch k overlaps conv of k+1)
     DevBuf boxes;                 // decoded [B, N, 5+NC] fp32
     DevBuf stage;
     bool loaded = false;
@@ -68,9 +69,9 @@ struct Net {
     ~Net();
     void build();
     void load(int n, const char* const* names, DLManagedTensor* const* tensors);
-    void forward(const float* in_dev, int b);   // NCHW fp32 on the device -> heads
+    void forward(const float* in_dev, int b, int head_set = 0);   // NCHW fp32 on the device -> heads[head_set]
     void decode(int b);                         // heads -> boxes
-    DecodeArgs decode_args(int b) const;        // for the fused decode+candidates path
+    DecodeArgs decode_args(int b, int head_set = 0) const;   // for the fused decode+candidates path
     std::string profile(int b, int iters);      // per-layer CSV report
 
   private:
