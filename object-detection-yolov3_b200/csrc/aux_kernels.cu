@@ -9,6 +9,7 @@
 //   k_heads_to_nchw   [B,HW,pitch] fp32 -> NCHW fp32 (the parity point of y3_forward_heads)
 //   k_decode          reorg_layer + convert_feature_map_to_inference_detections (model.py:122-212)
 #include "aux_kernels.cuh"
+#include <stdlib.h>
 
 namespace y3 {
 
@@ -97,6 +98,8 @@ k_stem(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, const floa
 
 void launch_stem(y3_context* ctx, const float* in, __nv_bfloat16* out, const float* w, const float* bias,
                  const float* scale, const float* shift, int B, int H, int W, int cin) {
+    static const bool use_tc = getenv("Y3_STEM_FP32") == nullptr;
+    if (use_tc && launch_stem_tc(ctx, in, out, w, bias, scale, shift, B, H, W, cin)) return;
     const long long npix = (long long)B * H * W / 2;        // two pixels per thread
     const int blocks = (int)std::min<long long>((npix + 127) / 128, (long long)ctx->sm_count * 64);
     if (cin == 1) k_stem<1><<<blocks, 128, 0, ctx->stream>>>(in, out, w, bias, scale, shift, B, H, W);

@@ -48,6 +48,9 @@ __device__ __forceinline__ float decode_corner(const DecodeArgs& D, const float*
 
 void launch_stem(y3_context* ctx, const float* in, __nv_bfloat16* out, const float* w, const float* bias,
                  const float* scale, const float* shift, int B, int H, int W, int cin);
+// tensor-core stem (stem_tc.cu); returns false when the channel count is not covered
+bool launch_stem_tc(y3_context* ctx, const float* in, __nv_bfloat16* out, const float* w, const float* bias, const float* scale,
+                    const float* shift, int B, int H, int W, int cin);
 void pack_conv_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, int taps, int cin, int cout, int cout_pad);
 void pack_convt_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, long long n);
 void compose_up(y3_context* ctx, const float* wy, const float* kt, const float* by, const float* bt, int c_up, int c_x, int c_r,
