@@ -282,6 +282,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             if (lane == 0) mbar_arrive(&tmem_empty[p]);
             if (!P.out_f32) {
                 fence_proxy_async_smem();                  // generic-proxy smem writes -> visible to TMA
+                // the store of the previous tile (other staging buffer) must have finished reading smem before
+                // ANY thread passes this barrier and starts writing that buffer for the next tile
+                if (warp == 2 && lane == 0 && !P.has_res) tma_store_wait_read();
                 named_bar_sync(1, 128);
                 if (warp == 2 && lane == 0) {
                     for (int ch = 0; ch < C::NCHUNK; ++ch)
@@ -290,9 +293,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     if (P.has_res) {
                         tma_store_wait_read();             // residual prefetch may overwrite this buffer
                         mbar_arrive(&stg_empty[p]);
-                    } else {
-                        tma_store_wait_read_keep1();       // double-buffered staging: only the buffer written
-                    }                                      // two tiles ago must be drained; this store overlaps
+                    }                                      // (no residual: drained lazily before the next barrier,
+                                                           //  so this store overlaps the next tile's epilogue)
 
                 }
             }

@@ -42,6 +42,7 @@ void encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64
 
 void launch_conv(y3_context* ctx, const ConvLaunch& L);
 void launch_conv2(y3_context* ctx, const ConvLaunch& L);
+bool launch_conv2h(y3_context* ctx, const ConvLaunch& L);   // half-staged variant (conv_tc2h.cu); false = not used
 
 }  // namespace y3
 

@@ -283,6 +283,8 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[p], 0));
             if (!P.out_f32) {
                 fence_proxy_async_smem();
+                // drain the previous tile's store (other staging buffer) before anyone may pass the barrier
+                if (warp == 2 && lane == 0 && !P.has_res && C::NSTG == 2) tma_store_wait_read();
                 named_bar_sync(1, 256);
                 if (warp == 2 && lane == 0) {
                     if (mt < m_tiles)
@@ -292,9 +294,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                     if (P.has_res || C::NSTG == 1) {
                         tma_store_wait_read();
                         if (P.has_res) mbar_arrive(&stg_empty[sp]);
-                    } else {
-                        tma_store_wait_read_keep1();          // overlap this store with the next tile's epilogue
-                    }
+                    }                                         // (no residual: drained lazily before the next barrier)
                 }
                 if (C::NSTG == 1) named_bar_sync(2, 256);     // single staging buffer: wait until it was read
             }
@@ -323,6 +323,7 @@ static void launch2_t(y3_context* ctx, const ConvLaunch& L) {
 }
 
 void launch_conv2(y3_context* ctx, const ConvLaunch& L) {
+    if (launch_conv2h(ctx, L)) return;
     static const int stg256 = getenv("Y3_CONV2_STG") ? atoi(getenv("Y3_CONV2_STG")) : 2;
     if (L.bn == 256 && stg256 == 1) launch2_t<256, 1>(ctx, L);
     else if (L.bn == 256) launch2_t<256, 2>(ctx, L);
