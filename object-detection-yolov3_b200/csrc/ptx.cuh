@@ -195,8 +195,12 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
     return r;
 }
+// Remote (or local) arrive through a shared::cluster address.  Default semantics (release at CTA scope):
+// the cluster-scope form (.release.cluster) costs a full cluster-wide memory fence per call (ncu: 22 % of the
+// stall samples of the 1x1 layers were stall_membar on it); the TMEM hand-off it is used for is ordered by
+// tcgen05.fence::before_thread_sync / after_thread_sync around the barrier, exactly as in CUTLASS.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads issued by either CTA of a pair; complete_tx lands on the barrier at cluster address `bar`
 __device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
