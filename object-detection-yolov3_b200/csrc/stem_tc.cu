@@ -22,7 +22,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_noswz(uint32_t saddr, uint32_
 }
 
 template <int CIN>
-__global__ void __launch_bounds__(128, 8)
+__global__ void __launch_bounds__(128, (CIN == 1) ? 8 : 6)
 k_stem_tc(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, const float* __restrict__ w /*[9*CIN][32]*/,
           const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift, int B, int H, int W) {
 #if defined(__CUDA_ARCH_FEAT_SM100_ALL) || defined(__CUDA_ARCH_FEAT_SM101_ALL)
@@ -65,14 +65,12 @@ k_stem_tc(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, const f
     const long long npix = (long long)B * H * W;
     const long long n_tiles = (npix + 127) / 128;
     uint32_t phase = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long pix = tile * 128 + tid;
-        const bool ok = pix < npix;
-        // ---- gather the taps of this thread's pixel
-        float v[KP];
+    // taps of this thread's pixel of tile `tile` (zeros outside the image = SAME padding)
+    auto gather = [&](long long tile, float (&v)[KP]) {
 #pragma unroll
         for (int k = 0; k < KP; ++k) v[k] = 0.f;
-        if (ok) {
+        const long long pix = tile * 128 + tid;
+        if (tile < n_tiles && pix < npix) {
             const int x = (int)(pix % W);
             const long long t = pix / W;
             const int y = (int)(t % H);
@@ -92,6 +90,14 @@ k_stem_tc(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, const f
                 }
             }
         }
+    };
+    float v[KP], vn[KP];
+    gather(blockIdx.x, vn);
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long pix = tile * 128 + tid;
+        const bool ok = pix < npix;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) v[k] = vn[k];
         unsigned char* rowp = sA + (tid >> 3) * SBO + (tid & 7) * 16;
 #pragma unroll
         for (int kc = 0; kc < KCH; ++kc) {
@@ -115,6 +121,7 @@ k_stem_tc(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, const f
                 umma_bf16(tmem_base, adesc + (uint64_t)(ks * 16), bdesc + (uint64_t)(ks * 16), idesc, (uint32_t)(ks != 0));
             umma_commit(&bar);
         }
+        gather(tile + gridDim.x, vn);          // next tile's loads fly while this tile's MMA + epilogue run
         mbar_wait(&bar, phase);
         phase ^= 1u;
         tc_fence_after();
@@ -153,7 +160,7 @@ bool launch_stem_tc(y3_context* ctx, const float* in, __nv_bfloat16* out, const 
                     const float* shift, int B, int H, int W, int cin) {
     if (cin != 1 && cin != 3) return false;                  // other channel counts use the FP32-pipe stem
     const long long n_tiles = ((long long)B * H * W + 127) / 128;
-    const int blocks = (int)std::min<long long>(n_tiles, (long long)ctx->sm_count * 8);
+    const int blocks = (int)std::min<long long>(n_tiles, (long long)ctx->sm_count * (cin == 1 ? 8 : 6));
     if (cin == 1) k_stem_tc<1><<<blocks, 128, 0, ctx->stream>>>(in, out, w, bias, scale, shift, B, H, W);
     else k_stem_tc<3><<<blocks, 128, 0, ctx->stream>>>(in, out, w, bias, scale, shift, B, H, W);
     Y3_LAUNCHED(ctx);
