@@ -401,6 +401,7 @@ static void launch_t(y3_context* ctx, const ConvLaunch& L) {
 }
 
 void launch_conv(y3_context* ctx, const ConvLaunch& L) {
+    if (L.halo) { launch_conv_halo(ctx, L); return; }
     if (L.two_cta) { launch_conv2(ctx, L); return; }
     if (L.bn == 128 && L.bk == 64) launch_t<128, 64>(ctx, L);
     else if (L.bn == 64 && L.bk == 64) launch_t<64, 64>(ctx, L);

@@ -33,6 +33,7 @@ struct ConvLaunch {
     ConvArgs args;
     int bn, bk;              // template selection (two_cta: bn = N of the pair UMMA, 128 or 256)
     int two_cta;             // use the cta_group::2 kernel (conv_tc2.cu)
+    int halo;                // weights-stationary halo-row kernel (conv_halo.cu): 3x3 s1, Cin 32/64
     int grid;
 };
 
@@ -43,6 +44,8 @@ void encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64
 void launch_conv(y3_context* ctx, const ConvLaunch& L);
 void launch_conv2(y3_context* ctx, const ConvLaunch& L);
 bool launch_conv2h(y3_context* ctx, const ConvLaunch& L);   // half-staged variant (conv_tc2h.cu); false = not used
+void launch_conv_halo(y3_context* ctx, const ConvLaunch& L);
+bool halo_supported(int cin, int cout_pad);
 
 }  // namespace y3
 

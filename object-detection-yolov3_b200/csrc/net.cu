@@ -283,6 +283,53 @@ void Net::make_launches(Op& op) {
         const long long pair_tiles_256 = ((m_rows / 128 + 1) / 2) * (op.cout_pad / 256 > 0 ? op.cout_pad / 256 : 1);
         if (small_opt && bn == 256 && op.k == 1 && pair_tiles_256 < 3LL * (ctx->sm_count / 2)) bn = 128;
     }
+    static const bool use_halo = getenv("Y3_NO_HALO") == nullptr;
+    if (use_halo && op.kind == Op::CONV && op.k == 3 && op.stride == 1 && op.cout == op.cout_pad && halo_supported(cin, op.cout_pad)) {
+        // shallow 3x3 layers: weights-stationary halo-row kernel (conv_halo.cu)
+        ConvLaunch L;
+        memset(&L, 0, sizeof(L));
+        ConvArgs& A = L.args;
+        L.halo = 1; L.two_cta = 1; L.bn = op.cout_pad; L.bk = cin;
+        A.taps = 9; A.kwn = 3; A.cin = cin; A.kchunks = 1; A.stride = 1; A.pad = 1; A.a_cpitch = pitch_in; A.k_split = 1;
+        A.has_res = op.res_t >= 0;
+        A.bias = op.bias.as<float>(); A.scale = op.scale.as<float>(); A.shift = op.shift.as<float>();
+        A.cout_valid = op.cout; A.n_tiles_n = 1;
+        A.Ho = ti.h; A.Wo = ti.w; A.BH = 1; A.BW = 128; A.tiles_x = (ti.w + 127) / 128;
+        op.flat = false;
+        {
+            uint64_t dims[4] = {(uint64_t)cin, (uint64_t)ti.w, (uint64_t)ti.h, (uint64_t)maxB};
+            uint64_t str[3] = {(uint64_t)pitch_in * 2, (uint64_t)ti.w * pitch_in * 2, (uint64_t)ti.h * ti.w * pitch_in * 2};
+            uint32_t box[4] = {(uint32_t)cin, 130, 1, 1};
+            encode_tmap_bf16(&L.map_a, in_base, 4, dims, str, box, cin * 2);
+            L.map_a2 = L.map_a;
+        }
+        {
+            uint64_t dims[2] = {(uint64_t)9 * cin, (uint64_t)op.cout_pad};
+            uint64_t str[1] = {(uint64_t)9 * cin * 2};
+            uint32_t box[2] = {(uint32_t)cin, (uint32_t)(op.cout_pad / 2)};
+            encode_tmap_bf16(&L.map_b, op.w.as<__nv_bfloat16>(), 2, dims, str, box, cin * 2);
+        }
+        {
+            const TensorInfo& to = tensors[op.out.t];
+            __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(to.ptr) + op.out.coff;
+            uint64_t dims[4] = {(uint64_t)op.cout, (uint64_t)to.w, (uint64_t)to.h, (uint64_t)maxB};
+            uint64_t str[3] = {(uint64_t)to.c * 2, (uint64_t)to.w * to.c * 2, (uint64_t)to.h * to.w * to.c * 2};
+            uint32_t box[4] = {64, 128, 1, 1};
+            encode_tmap_bf16(&L.map_out, obase, 4, dims, str, box, 128);
+        }
+        if (A.has_res) {
+            const TensorInfo& tr = tensors[op.res.t];
+            const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(tr.ptr) + op.res.coff;
+            uint64_t dims[4] = {(uint64_t)op.res.c, (uint64_t)tr.w, (uint64_t)tr.h, (uint64_t)maxB};
+            uint64_t str[3] = {(uint64_t)tr.c * 2, (uint64_t)tr.w * tr.c * 2, (uint64_t)tr.h * tr.w * tr.c * 2};
+            uint32_t box[4] = {64, 128, 1, 1};
+            encode_tmap_bf16(&L.map_res, rbase, 4, dims, str, box, 128);
+        } else {
+            L.map_res = L.map_out;
+        }
+        op.launches.push_back(L);
+        return;
+    }
     const int oc = bn < 64 ? bn : 64;
     const bool phased = (op.kind == Op::CONVT || op.kind == Op::UPCONV);   // 4 launches, one per output phase (i,j)
     const int n_sub = phased ? 4 : 1;
@@ -425,6 +472,12 @@ void Net::make_launches(Op& op) {
 void Net::set_batch(Op& op, int b) {
     for (ConvLaunch& L : op.launches) {
         ConvArgs& A = L.args;
+        if (L.halo) {
+            A.n_img = b; A.tiles_y = A.Ho; A.tiles_per_img = A.tiles_x * A.Ho;
+            A.total_tiles = A.tiles_per_img * b;
+            L.grid = 0;      // chosen by launch_conv_halo
+            continue;
+        }
         if (op.flat) {
             const long long M = (long long)b * op.pix_per_img;
             A.Wo = (int)M;
