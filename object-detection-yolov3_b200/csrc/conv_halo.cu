@@ -27,12 +27,13 @@ using namespace ptx;
 
 static constexpr int HALO_THREADS = 64 + 256;
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, int STRIDE>
 struct HaloCfg {
     static constexpr int ROWB = CIN * 2;                              // bytes of one pixel = one K-major row
-    static constexpr int HPX = 130;                                   // pixels per ring slot
+    static constexpr int HPX = (STRIDE == 1) ? 130 : 128;             // pixels per ring slot
     static constexpr int SLOT = ((HPX * ROWB + 1023) / 1024) * 1024;
-    static constexpr int S = (CIN == 32) ? 6 : 5;                     // ring slots (3 live + prefetch)
+    // stride 1: ring of input rows (3 live + prefetch); stride 2: ring of per-tap im2col tiles
+    static constexpr int S = (STRIDE == 1) ? ((CIN == 32) ? 6 : 5) : ((CIN == 32) ? 7 : 5);
     static constexpr int WTAP = (COUT / 2) * ROWB;                    // this CTA's half of one tap
     static constexpr int W_BYTES = 9 * WTAP;
     static constexpr int NCHUNK = COUT / 64;
@@ -54,12 +55,12 @@ __device__ __forceinline__ uint32_t pack2h(float lo, float hi) {
 }
 
 // P.tiles_x = segments per row, P.Ho/P.Wo = output grid, P.n_img = images of this launch
-template <int CIN, int COUT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO_THREADS, HaloCfg<CIN, COUT>::CTAS_PER_SM)
+template <int CIN, int COUT, int STRIDE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HALO_THREADS, HaloCfg<CIN, COUT, STRIDE>::CTAS_PER_SM)
 k_conv_halo(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, const ConvArgs P) {
 #if defined(__CUDA_ARCH_FEAT_SM100_ALL) || defined(__CUDA_ARCH_FEAT_SM101_ALL)
-    using C = HaloCfg<CIN, COUT>;
+    using C = HaloCfg<CIN, COUT, STRIDE>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* w_base = smem;
@@ -122,6 +123,32 @@ k_conv_halo(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             }
             int k = 0;                                  // running input-row load index (ring position)
             int it = 0;                                 // running tile index
+            if (STRIDE == 2) {
+                // stride 2: the A operand of every tap is an im2col-mode load of 128 output pixels (padding 0 before /
+                // 1 after and the traversal stride live in the map); only the weights are stationary
+                for (int t = t_begin; t < t_end; ++t, ++it) {
+                    const int col = t / Ho;
+                    const int h = t - col * Ho;
+                    const int ip = col / P.tiles_x;
+                    const int w0 = (col - ip * P.tiles_x) * 128;
+                    const int img = 2 * ip + (int)rank;
+                    if (P.has_res) {
+                        const int p = it & 1;
+                        const uint32_t use = (uint32_t)(it >> 1);
+                        mbar_wait(&stg_empty[p], (use & 1u) ^ 1u);
+                        mbar_expect_tx(&res_full[p], (uint32_t)C::STG_BYTES);
+                        for (int ch = 0; ch < C::NCHUNK; ++ch)
+                            tma_load_4d(stg_base + p * C::STG_BYTES + ch * C::CHUNK_BYTES, &map_res, &res_full[p], ch * 64, w0, h, img);
+                    }
+                    for (int tap = 0; tap < 9; ++tap, ++k) {
+                        const int slot = k % C::S;
+                        mbar_wait(&empty[slot], (uint32_t)(((k / C::S) & 1) ^ 1));
+                        if (rank == 0) mbar_expect_tx(&full[slot], (uint32_t)(2 * C::HPX * C::ROWB));
+                        tma2_load_im2col_4d(ring + slot * C::SLOT, &map_a, mapa_u32(&full[slot], 0), 0, 2 * w0, 2 * h, img,
+                                            (uint16_t)(tap % 3), (uint16_t)(tap / 3));
+                    }
+                }
+            } else
             for (int t = t_begin; t < t_end;) {
                 const int col = t / Ho;
                 const int h0 = t - col * Ho;
@@ -161,6 +188,28 @@ k_conv_halo(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             const uint32_t ring_addr = smem_u32(ring);
             int k0 = 0;
             int it = 0;
+            if (STRIDE == 2) {
+                for (int t = t_begin; t < t_end; ++t, ++it) {
+                    const int p = it & 1;
+                    const uint32_t use = (uint32_t)(it >> 1);
+                    mbar_wait(&tmem_empty[p], (use & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(p * COUT);
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap, ++k0) {
+                        const int slot = k0 % C::S;
+                        mbar_wait(&full[slot], (uint32_t)((k0 / C::S) & 1));
+                        tc_fence_after();
+                        const uint64_t adesc = make_smem_desc(ring_addr + (uint32_t)(slot * C::SLOT), C::SBO, C::SWZ);
+                        const uint64_t bdesc = make_smem_desc(w_addr + (uint32_t)(tap * C::WTAP), C::SBO, C::SWZ);
+#pragma unroll
+                        for (int kc = 0; kc < CIN / 16; ++kc)
+                            umma2_bf16(d_tmem, adesc + (uint64_t)(kc * 2), bdesc + (uint64_t)(kc * 2), idesc, (uint32_t)((tap | kc) != 0));
+                        umma2_commit_mc(&empty[slot], 3);
+                    }
+                    umma2_commit_mc(&tmem_full[p], 3);
+                }
+            } else
             for (int t = t_begin; t < t_end;) {
                 const int col = t / Ho;
                 const int h0 = t - col * Ho;
@@ -291,27 +340,30 @@ k_conv_halo(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #endif
 }
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, int STRIDE>
 static void launch_halo_t(y3_context* ctx, const ConvLaunch& L) {
-    using C = HaloCfg<CIN, COUT>;
+    using C = HaloCfg<CIN, COUT, STRIDE>;
     static bool attr[64] = {};
     if (!attr[ctx->device & 63]) {
-        Y3_CUDA(cudaFuncSetAttribute(k_conv_halo<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        Y3_CUDA(cudaFuncSetAttribute(k_conv_halo<CIN, COUT, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr[ctx->device & 63] = true;
     }
     const ConvArgs& A = L.args;
     const long long total = (long long)((A.n_img + 1) / 2) * A.tiles_x * A.Ho;
     const int pairs = (int)std::min<long long>(total, (long long)(ctx->sm_count / 2) * C::CTAS_PER_SM);
-    k_conv_halo<CIN, COUT><<<2 * pairs, HALO_THREADS, C::SMEM, ctx->stream>>>(L.map_a, L.map_b, L.map_out, L.map_res, L.args);
+    k_conv_halo<CIN, COUT, STRIDE><<<2 * pairs, HALO_THREADS, C::SMEM, ctx->stream>>>(L.map_a, L.map_b, L.map_out, L.map_res, L.args);
     Y3_LAUNCHED(ctx);
 }
 
 bool halo_supported(int cin, int cout_pad) { return (cin == 32 && cout_pad == 64) || (cin == 64 && cout_pad == 128); }
 
 void launch_conv_halo(y3_context* ctx, const ConvLaunch& L) {
-    if (L.args.cin == 32 && L.bn == 64) launch_halo_t<32, 64>(ctx, L);
-    else if (L.args.cin == 64 && L.bn == 128) launch_halo_t<64, 128>(ctx, L);
-    else fail(Y3_ERR_UNSUPPORTED, "no halo conv kernel for Cin=%d Cout=%d", L.args.cin, L.bn);
+    const int s = L.args.stride;
+    if (L.args.cin == 32 && L.bn == 64 && s == 1) launch_halo_t<32, 64, 1>(ctx, L);
+    else if (L.args.cin == 64 && L.bn == 128 && s == 1) launch_halo_t<64, 128, 1>(ctx, L);
+    else if (L.args.cin == 32 && L.bn == 64 && s == 2) launch_halo_t<32, 64, 2>(ctx, L);
+    else if (L.args.cin == 64 && L.bn == 128 && s == 2) launch_halo_t<64, 128, 2>(ctx, L);
+    else fail(Y3_ERR_UNSUPPORTED, "no halo conv kernel for Cin=%d Cout=%d stride %d", L.args.cin, L.bn, s);
 }
 
 }  // namespace y3

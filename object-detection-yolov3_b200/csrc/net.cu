@@ -284,23 +284,29 @@ void Net::make_launches(Op& op) {
         if (small_opt && bn == 256 && op.k == 1 && pair_tiles_256 < 3LL * (ctx->sm_count / 2)) bn = 128;
     }
     static const bool use_halo = getenv("Y3_NO_HALO") == nullptr;
-    if (use_halo && op.kind == Op::CONV && op.k == 3 && op.stride == 1 && op.cout == op.cout_pad && halo_supported(cin, op.cout_pad)) {
+    static const bool use_ws2 = getenv("Y3_NO_WS2") == nullptr;
+    if (use_halo && op.kind == Op::CONV && op.k == 3 && (op.stride == 1 || use_ws2) && op.cout == op.cout_pad && halo_supported(cin, op.cout_pad)) {
         // shallow 3x3 layers: weights-stationary halo-row kernel (conv_halo.cu)
         ConvLaunch L;
         memset(&L, 0, sizeof(L));
         ConvArgs& A = L.args;
         L.halo = 1; L.two_cta = 1; L.bn = op.cout_pad; L.bk = cin;
-        A.taps = 9; A.kwn = 3; A.cin = cin; A.kchunks = 1; A.stride = 1; A.pad = 1; A.a_cpitch = pitch_in; A.k_split = 1;
+        A.taps = 9; A.kwn = 3; A.cin = cin; A.kchunks = 1; A.stride = op.stride; A.pad = op.stride == 1 ? 1 : 0; A.a_cpitch = pitch_in; A.k_split = 1;
         A.has_res = op.res_t >= 0;
         A.bias = op.bias.as<float>(); A.scale = op.scale.as<float>(); A.shift = op.shift.as<float>();
         A.cout_valid = op.cout; A.n_tiles_n = 1;
-        A.Ho = ti.h; A.Wo = ti.w; A.BH = 1; A.BW = 128; A.tiles_x = (ti.w + 127) / 128;
+        A.Ho = ti.h / op.stride; A.Wo = ti.w / op.stride; A.BH = 1; A.BW = 128; A.tiles_x = (A.Wo + 127) / 128;
         op.flat = false;
         {
             uint64_t dims[4] = {(uint64_t)cin, (uint64_t)ti.w, (uint64_t)ti.h, (uint64_t)maxB};
             uint64_t str[3] = {(uint64_t)pitch_in * 2, (uint64_t)ti.w * pitch_in * 2, (uint64_t)ti.h * ti.w * pitch_in * 2};
-            uint32_t box[4] = {(uint32_t)cin, 130, 1, 1};
-            encode_tmap_bf16(&L.map_a, in_base, 4, dims, str, box, cin * 2);
+            if (op.stride == 1) {
+                uint32_t box[4] = {(uint32_t)cin, 130, 1, 1};
+                encode_tmap_bf16(&L.map_a, in_base, 4, dims, str, box, cin * 2);
+            } else {
+                int lower[2] = {0, 0}, upper[2] = {-1, -1};          // TF SAME, stride 2: pad 0 before, 1 after
+                encode_tmap_im2col_bf16(&L.map_a, in_base, dims, str, lower, upper, (uint32_t)cin, 128, 2, cin * 2);
+            }
             L.map_a2 = L.map_a;
         }
         {
