@@ -23,6 +23,11 @@ from yolo3_b200 import infer_tiled_distributed, post_engine, tile_plan
 
 BATCH_SIZE = 64          # tiles per forward batch (declared but unused in the reference)
 EDGE_EFFECT_RANGE = 96
+# Optional extra stage, off by default because the reference has none (seams are resolved by centre ownership
+# only): greedy per-class NMS among the final boxes that straddle a tile-zone boundary.  Set the constant or
+# Y3_CROSS_SEAM_NMS=1 to enable.
+CROSS_SEAM_NMS = os.environ.get("Y3_CROSS_SEAM_NMS", "0") not in ("", "0")
+CROSS_SEAM_IOU_THRESHOLD = 0.3
 
 
 def convert_image_to_tiles(img, tile_size):
@@ -44,7 +49,10 @@ def _distributed():
 
 def inference_image_tiled(yolo_model, img, tile_size, min_roi_size):
     img = np.ascontiguousarray(img)
-    engine = getattr(yolo_model, "engine", None)
+    if hasattr(yolo_model, "engine_for"):
+        engine = yolo_model.engine_for(tile_size)
+    else:
+        engine = getattr(yolo_model, "engine", None)
     if engine is not None and tuple(tile_size) == tuple(engine.img_size[:2]):
         if _distributed():
             pred = infer_tiled_distributed(engine, img, tile_size, min_roi_size, EDGE_EFFECT_RANGE).cpu().numpy()
@@ -57,6 +65,9 @@ def inference_image_tiled(yolo_model, img, tile_size, min_roi_size):
         tiles = post.tiles_normalized(img, tile_size, EDGE_EFFECT_RANGE)
         dets = np.stack([np.asarray(yolo_model(t[None], training=False))[0] for t in tiles])
         pred = post.stitch_tiles(dets, img.shape[:2], tile_size, min_roi_size, EDGE_EFFECT_RANGE)
+    if CROSS_SEAM_NMS:
+        nms_engine = engine if engine is not None else post_engine()
+        pred = nms_engine.cross_seam_nms(pred, img.shape[:2], tile_size, EDGE_EFFECT_RANGE, CROSS_SEAM_IOU_THRESHOLD)
     print('Found: {} rois'.format(pred.shape[0]))
     return pred
 

@@ -66,18 +66,39 @@ class YoloV3:
 
 class LoadedModel:
     """What `tf.saved_model.load(path)` is to the reference scripts: callable as
-    yolo_model(batch, training=False) -> [B, N, 5+NC]; also carries the engine for the fused paths."""
+    yolo_model(batch, training=False) -> [B, N, 5+NC]; also carries the engine for the fused paths.
+    Reads the reference's TF SavedModel directory (variable bundle parsed without TensorFlow) or the
+    y3_config.json + y3_weights.npz side-car format.  The network is fully convolutional: when the model
+    directory does not pin the input size the engine is built for the first size it is asked for."""
 
     def __init__(self, saved_model_filepath, max_batch=1, device=0):
         cfg, w = _weights.load_model_dir(saved_model_filepath)
-        self.img_size = tuple(cfg["img_size"])
+        self._weights, self._max_batch, self._device = w, max_batch, device
+        self._c_img = int(cfg["img_size"][2])
         self.number_classes = int(cfg["number_classes"])
         self.anchors = [tuple(a) for a in cfg["anchors"]]
-        self.engine = Engine(self.img_size, self.number_classes, self.anchors, max_batch=max_batch, device=device)
-        self.engine.load_weights(w)
+        self._engines = {}
+        self.engine = None
+        self.img_size = None
+        if cfg["img_size"][0] and cfg["img_size"][1]:
+            self.engine_for(cfg["img_size"][:2])
+
+    def engine_for(self, hw):
+        """the engine for H x W inputs (built on first use, weights uploaded once per size)"""
+        key = (int(hw[0]), int(hw[1]))
+        if key not in self._engines:
+            eng = Engine(key + (self._c_img,), self.number_classes, self.anchors, max_batch=self._max_batch, device=self._device)
+            eng.load_weights(self._weights)
+            self._engines[key] = eng
+        self.engine = self._engines[key]
+        self.img_size = key + (self._c_img,)
+        return self.engine
 
     def __call__(self, batch, training=False):
-        return self.engine.forward_boxes(np.ascontiguousarray(np.asarray(batch), dtype=np.float32))
+        if training:
+            raise NotImplementedError("the B200 path is inference-only")
+        batch = np.ascontiguousarray(np.asarray(batch), dtype=np.float32)
+        return self.engine_for(batch.shape[2:4]).forward_boxes(batch)
 
 
 def load_saved_model(saved_model_filepath, max_batch=1, device=0):

@@ -201,6 +201,29 @@ class Engine:
             return out[:n.value]
 
     # ------------------------------------------------------------------ post-processing
+    def cross_seam_nms(self, pred, img_hw, tile_size, edge_range=96, iou_threshold=0.3):
+        """Optional final stage (north_star; NOT in the reference, which resolves seams by centre ownership
+        only, inference_tiled.py:235-254): boxes whose extent crosses a zone boundary of the tile grid are
+        candidates, greedy per-class NMS (y3_single_class_nms on the GPU) runs among them, suppressed rows
+        are dropped, everything else and the row order are untouched.  pred: float64 [n,6] as returned by
+        infer_tiled -> float64 [n',6]."""
+        pred = np.asarray(pred, np.float64)
+        cand = seam_candidates(pred, img_hw, tile_size, edge_range)
+        if not cand.any():
+            return pred
+        drop = np.zeros(pred.shape[0], bool)
+        rows = np.nonzero(cand)[0]
+        labels = pred[rows, 5]
+        for c in np.unique(labels):
+            r = rows[labels == c]
+            if r.size < 2:
+                continue
+            keep = self.single_class_nms(pred[r, 0:4].astype(np.float32), pred[r, 4].astype(np.float32), iou_threshold)
+            gone = np.ones(r.size, bool)
+            gone[np.asarray(keep, np.int64)] = False
+            drop[r[gone]] = True
+        return pred[~drop]
+
     def compute_iou(self, box, boxes):
         box = np.ascontiguousarray(box, dtype=np.float32)
         boxes = np.ascontiguousarray(boxes, dtype=np.float32)
@@ -284,6 +307,19 @@ def _torch_dtype(t):
     import torch
     return {torch.uint8: _lib.U8, torch.int32: _lib.I32, torch.float32: _lib.F32,
             getattr(torch, "uint16", None): _lib.U16, torch.int16: _lib.U16}[t.dtype]
+
+
+def seam_candidates(pred, img_hw, tile_size, edge_range):
+    """Rows of pred [n,6] (integer pixel corners, inclusive) that straddle a zone boundary of the tile grid
+    (zone = tile - 2*edge_range on every axis that is actually tiled, inference_tiled.py:41-47)."""
+    pred = np.asarray(pred)
+    cand = np.zeros(pred.shape[0], bool)
+    for axis, (lo, hi) in enumerate(((1, 3), (0, 2))):           # axis 0 = rows (y), axis 1 = columns (x)
+        if int(tile_size[axis]) >= int(img_hw[axis]):
+            continue
+        zone = int(tile_size[axis]) - 2 * int(edge_range)
+        cand |= np.floor_divide(pred[:, lo], zone) != np.floor_divide(pred[:, hi], zone)
+    return cand
 
 
 def tile_count(img_h, img_w, tile_size, edge_range):

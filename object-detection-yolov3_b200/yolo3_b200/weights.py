@@ -3,10 +3,13 @@ Keras-default random initialisation (what `model.YoloV3(...)` gives before train
 TensorFlow-free on-disk format for `--saved-model-filepath`.
 
 The reference keeps weights in a TF SavedModel (train.py:221, inference.py:35).  TensorFlow is not
-available here, so a model directory is:
+available here, so a model directory is either
+  * the reference's own SavedModel: `saved_model.pb` + `variables/variables.{index,data-*}` - the variable bundle
+    is parsed without TensorFlow by tf_bundle.py (anchors are graph constants that the bundle does not hold: they
+    come from an optional y3_config.json next to saved_model.pb, else the reference defaults of model.py:433), or
+  * the TensorFlow-free side-car format written by save_model_dir():
     <dir>/y3_config.json     {"img_size":[H,W,C], "number_classes":NC, "anchors":[[w,h],...]}
     <dir>/y3_weights.npz     one fp32 array per Keras variable name, Keras layouts
-Reading the SavedModel's own `variables/` tensor bundle is the next item of SURVEY.md section 8(f).
 """
 import json
 import math
@@ -113,17 +116,50 @@ def save_model_dir(path, weights, img_size, number_classes, anchors):
 
 
 def load_model_dir(path):
-    """-> (config dict, {name: fp32 array}).  Raises with a precise message for a raw TF SavedModel."""
+    """-> (config dict, {name: fp32 array}).  cfg["img_size"] may hold None for H/W when the directory is a
+    TF SavedModel whose signature does not pin them (the engine is then built for the size it is called with)."""
     cfg_p, w_p = os.path.join(path, CONFIG_FILE), os.path.join(path, WEIGHTS_FILE)
-    if not (os.path.exists(cfg_p) and os.path.exists(w_p)):
-        if os.path.exists(os.path.join(path, "saved_model.pb")):
-            raise RuntimeError(
-                "%s is a TensorFlow SavedModel without the %s / %s side-car.  Reading the TF variable bundle "
-                "without TensorFlow is not implemented yet; export the Keras variables with "
-                "yolo3_b200.weights.save_model_dir()." % (path, CONFIG_FILE, WEIGHTS_FILE))
-        raise RuntimeError("%s does not contain %s and %s" % (path, CONFIG_FILE, WEIGHTS_FILE))
-    with open(cfg_p) as fh:
-        cfg = json.load(fh)
-    with np.load(w_p) as z:
-        weights = {k: z[k] for k in z.files}
-    return cfg, weights
+    cfg = None
+    if os.path.exists(cfg_p):
+        with open(cfg_p) as fh:
+            cfg = json.load(fh)
+    if cfg is not None and os.path.exists(w_p):
+        with np.load(w_p) as z:
+            weights = {k: z[k] for k in z.files}
+        return cfg, weights
+    prefix = os.path.join(path, "variables", "variables")
+    if os.path.exists(prefix + ".index"):
+        return _load_tf_saved_model(path, prefix, cfg)
+    raise RuntimeError("%s holds neither %s + %s nor a TensorFlow SavedModel (variables/variables.index)"
+                       % (path, CONFIG_FILE, WEIGHTS_FILE))
+
+
+def _load_tf_saved_model(path, prefix, cfg):
+    from . import tf_bundle
+    from .engine import DEFAULT_ANCHORS
+    found = tf_bundle.read_keras_variables(prefix)
+    stem = found.get("conv2d/kernel")
+    head = found.get("feature_map_1/kernel")
+    if stem is None or head is None or stem.ndim != 4 or head.ndim != 4:
+        raise RuntimeError("%s: the variable bundle does not hold the YOLOv3 layers (conv2d/kernel, feature_map_1/kernel)" % path)
+    c_img, det_c = int(stem.shape[2]), int(head.shape[3])
+    anchors = [tuple(a) for a in cfg["anchors"]] if cfg and "anchors" in cfg else list(DEFAULT_ANCHORS)
+    if det_c % len(anchors) or det_c // len(anchors) < 6:
+        raise RuntimeError("%s: %d detection channels do not fit %d anchors; put the training anchors into %s"
+                           % (path, det_c, len(anchors), CONFIG_FILE))
+    nc = det_c // len(anchors) - 5
+    weights = {}
+    for name, shape in variable_inventory(c_img, nc, len(anchors)):
+        if name not in found:
+            raise RuntimeError("%s: variable %s is missing from the SavedModel bundle" % (path, name))
+        if tuple(found[name].shape) != tuple(shape):
+            raise RuntimeError("%s: variable %s has shape %s, expected %s" % (path, name, found[name].shape, shape))
+        weights[name] = np.ascontiguousarray(found[name], np.float32)
+    hw = [None, None]
+    if cfg and "img_size" in cfg:
+        hw = [int(cfg["img_size"][0]), int(cfg["img_size"][1])]
+    else:
+        sig = tf_bundle.signature_input_shape(os.path.join(path, "saved_model.pb"))       # [-1, C, H, W]
+        if sig and sig[2] > 0 and sig[3] > 0:
+            hw = [int(sig[2]), int(sig[3])]
+    return {"img_size": [hw[0], hw[1], c_img], "number_classes": nc, "anchors": [[float(a), float(b)] for a, b in anchors]}, weights

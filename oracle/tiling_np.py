@@ -162,3 +162,31 @@ def tiled_inference_single_tile(model_fn, img, tile_size, min_roi_size, edge_ran
     b[:, 3] += oy
     b, s, l = finish_boxes(b, s, l, (H, W))
     return np.concatenate((b.astype(np.float64), s.astype(np.float64)[:, None], l.astype(np.float64)[:, None]), axis=1)
+
+
+def seam_candidates(pred, img_hw, tile_size, edge_range):
+    """Rows of the final [n,6] result whose inclusive integer extent straddles a zone boundary."""
+    pred = np.asarray(pred)
+    cand = np.zeros(pred.shape[0], bool)
+    for axis, (lo, hi) in enumerate(((1, 3), (0, 2))):
+        if int(tile_size[axis]) >= int(img_hw[axis]):
+            continue
+        zone = int(tile_size[axis]) - 2 * int(edge_range)
+        cand |= (pred[:, lo] // zone) != (pred[:, hi] // zone)
+    return cand
+
+
+def cross_seam_nms(pred, img_hw, tile_size, edge_range=96, iou_threshold=0.3):
+    """Optional stage that is NOT in the reference (north_star's cross-seam NMS): greedy per-class NMS
+    (the pinned greedy_nms, tie rule score desc / row asc) among the seam candidates only."""
+    pred = np.asarray(pred, np.float64)
+    cand = seam_candidates(pred, img_hw, tile_size, edge_range)
+    drop = np.zeros(pred.shape[0], bool)
+    rows = np.nonzero(cand)[0]
+    for c in np.unique(pred[rows, 5]):
+        r = rows[pred[rows, 5] == c]
+        kept = pp.greedy_nms(pred[r, 0:4].astype(F32), pred[r, 4].astype(F32), iou_threshold)
+        gone = np.ones(r.size, bool)
+        gone[kept] = False
+        drop[r[gone]] = True
+    return pred[~drop]

@@ -122,3 +122,35 @@ def test_inference_single_image_folder_and_cli(tmp_path):
     assert (out2 / "one.csv").read_text() == (out_dir / "one.csv").read_text()
     # bbox_utils facade == oracle on the same rows
     assert bbox_utils.single_class_nms(f[:200, :4], f[:200, 4], 0.3) == nms_c.greedy_nms(f[:200, :4], f[:200, 4], 0.3)
+
+
+def test_tf_saved_model_directory_is_a_drop_in(tmp_path):
+    """--saved-model-filepath pointing at the reference's own format (saved_model.pb + variables/ bundle, train.py:221),
+    read without TensorFlow, gives the same CSV as the side-car format holding the same variables."""
+    import cv2
+    import inference_tiled
+    from yolo3_b200 import tf_bundle
+    side_dir, tf_dir, img_dir = tmp_path / "side", tmp_path / "saved_model", tmp_path / "images"
+    img_dir.mkdir()
+    w = make_model_dir(str(side_dir), (256, 256, 1), 2)
+    tf_bundle.write_saved_model_variables(str(tf_dir), w, input_shape=[-1, 1, 256, 256], checksum_limit=1 << 16)
+    import json
+    json.dump({"anchors": [[32, 32], [64, 64], [128, 128]]}, open(str(tf_dir / "y3_config.json"), "w"))
+    img = cases.synthetic_image(600, 520, 1, np.uint16, seed=5, blobs=12)
+    assert cv2.imwrite(str(img_dir / "a.tif"), img[:, :, 0])
+    inference_tiled.inference_image_folder(str(img_dir), "tif", str(side_dir), str(tmp_path / "o1"), [256, 256], 24)
+    inference_tiled.inference_image_folder(str(img_dir), "tif", str(tf_dir), str(tmp_path / "o2"), [256, 256], 24)
+    a, b = (tmp_path / "o1" / "a.csv").read_text(), (tmp_path / "o2" / "a.csv").read_text()
+    assert a == b and a.count("\n") > 3
+    # a model directory that does not pin the input size serves any tile size (the network is fully convolutional)
+    os.remove(str(tf_dir / "saved_model.pb"))
+    inference_tiled.inference_image_folder(str(img_dir), "tif", str(tf_dir), str(tmp_path / "o3"), [256, 256], 24)
+    assert (tmp_path / "o3" / "a.csv").read_text() == a
+    # the optional cross-seam stage can only remove rows
+    inference_tiled.CROSS_SEAM_NMS = True
+    try:
+        inference_tiled.inference_image_folder(str(img_dir), "tif", str(side_dir), str(tmp_path / "o4"), [256, 256], 24)
+    finally:
+        inference_tiled.CROSS_SEAM_NMS = False
+    rows4 = (tmp_path / "o4" / "a.csv").read_text().splitlines()
+    assert set(rows4) <= set(a.splitlines()) and len(rows4) >= 2

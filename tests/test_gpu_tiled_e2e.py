@@ -8,7 +8,7 @@ Exactness split (DESIGN.md "parity"):
 import numpy as np
 import pytest
 
-from oracle import cases, nms_c, tiling_np as tl
+from oracle import cases, nms_c, postproc_np as pp, tiling_np as tl
 
 pytestmark = pytest.mark.gpu
 
@@ -55,3 +55,23 @@ def test_infer_tiled_equals_oracle_pipeline_on_gpu_boxes(shape, edge, batch):
     parts = [eng.infer_tiled(img, TILE, 24, edge_range=edge, tile_first=f, tile_count=c)
              for f, c in (shard_range(len(tiles), r, 3) for r in range(3))]
     assert np.array_equal(np.concatenate(parts), want)
+
+
+def test_cross_seam_nms_matches_oracle():
+    """optional stage (not in the reference): GPU NMS among the seam-straddling final boxes == oracle stage"""
+    rng = np.random.default_rng(11)
+    H, W, tile, edge = 1500, 1700, (512, 512), 96
+    n = 6000
+    cx, cy = rng.uniform(0, W, n), rng.uniform(0, H, n)
+    w, h = rng.uniform(20, 120, n), rng.uniform(20, 120, n)
+    pred = np.stack([np.clip(np.round(cx - w / 2), 0, W - 1), np.clip(np.round(cy - h / 2), 0, H - 1),
+                     np.clip(np.round(cx + w / 2), 0, W - 1), np.clip(np.round(cy + h / 2), 0, H - 1),
+                     pp.make_tie_free_scores(n, rng).astype(np.float64), rng.integers(0, 3, n).astype(np.float64)], axis=1)
+    from yolo3_b200 import post_engine, seam_candidates
+    cand = seam_candidates(pred, (H, W), tile, edge)
+    assert np.array_equal(cand, tl.seam_candidates(pred, (H, W), tile, edge)) and 100 < cand.sum() < n
+    got = post_engine().cross_seam_nms(pred, (H, W), tile, edge, 0.3)
+    want = tl.cross_seam_nms(pred, (H, W), tile, edge, 0.3)
+    assert got.shape[0] < n and np.array_equal(got, want)
+    # rows that do not straddle a seam are never touched
+    assert np.array_equal(got[~seam_candidates(got, (H, W), tile, edge)], pred[~cand])

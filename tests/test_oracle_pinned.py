@@ -45,3 +45,20 @@ def test_tiled_vs_reference(reference, edge, tile, shape):
     assert np.array_equal(ref, got) and ref.shape[0] > 0
     t_got, xg, yg = tl.cut_tiles(img, tile, edge)
     assert xs == xg and ys == yg and all(np.array_equal(a, b) for a, b in zip(t_ref, t_got))
+
+
+def test_cross_seam_stage_only_touches_seam_boxes():
+    """oracle of the optional cross-seam NMS stage (not in the reference): a duplicate pair straddling a seam
+    loses its lower-scored box, identical duplicates away from any seam are left alone"""
+    from oracle import tiling_np as tl
+    H, W, tile, edge = 1000, 1000, (512, 512), 96           # zone 320 -> seams at 320, 640, 960
+    pred = np.array([[300, 100, 340, 140, 0.9, 0], [301, 101, 341, 141, 0.8, 0],       # straddle x = 320: duplicate
+                     [300, 100, 340, 140, 0.7, 1],                                       # other class: kept
+                     [100, 100, 140, 140, 0.9, 0], [101, 101, 141, 141, 0.8, 0],         # no seam: untouched
+                     [100, 630, 140, 650, 0.6, 0], [100, 631, 141, 651, 0.5, 0]], np.float64)   # straddle y = 640
+    cand = tl.seam_candidates(pred, (H, W), tile, edge)
+    assert cand.tolist() == [True, True, True, False, False, True, True]
+    out = tl.cross_seam_nms(pred, (H, W), tile, edge, 0.3)
+    assert np.array_equal(out, pred[[0, 2, 3, 4, 5]])
+    # an axis that is not tiled has no seams
+    assert not tl.seam_candidates(pred, (400, 1000), tile, edge)[5:].any()
