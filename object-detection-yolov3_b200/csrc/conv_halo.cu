@@ -40,7 +40,8 @@ struct HaloCfg {
     static constexpr int CHUNK_BYTES = 128 * 128;
     static constexpr int STG_BYTES = 128 * COUT * 2;
     static constexpr int BAR_BYTES = (2 * S + 10) * 8 + 16;
-    static constexpr int SMEM = 1024 + W_BYTES + S * SLOT + 2 * STG_BYTES + BAR_BYTES;
+    static constexpr int PAR_BYTES = 3 * COUT * 4;                    // bias | scale | shift
+    static constexpr int SMEM = 1024 + W_BYTES + S * SLOT + 2 * STG_BYTES + PAR_BYTES + BAR_BYTES;
     static constexpr int CTAS_PER_SM = (CIN == 32) ? 2 : 1;
     static constexpr uint32_t TMEM_COLS = 2 * COUT;
     static constexpr uint32_t SWZ = (CIN == 64) ? (uint32_t)SWZ_128B : (uint32_t)SWZ_64B;
@@ -66,7 +67,8 @@ k_conv_halo(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     unsigned char* w_base = smem;
     unsigned char* ring = smem + C::W_BYTES;
     unsigned char* stg_base = ring + C::S * C::SLOT;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + 2 * C::STG_BYTES);
+    float* s_par = reinterpret_cast<float*>(stg_base + 2 * C::STG_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + 2 * C::STG_BYTES + C::PAR_BYTES);
     uint64_t* full = bars;                       // leader only: both CTAs' row loads land here
     uint64_t* empty = bars + C::S;               // per CTA, multicast commit
     uint64_t* tmem_full = bars + 2 * C::S;       // per CTA, multicast commit
@@ -100,6 +102,9 @@ k_conv_halo(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc2<C::TMEM_COLS>(tmem_slot);
+    for (int i = threadIdx.x; i < COUT; i += HALO_THREADS) {
+        s_par[i] = P.bias[i]; s_par[COUT + i] = P.scale[i]; s_par[2 * COUT + i] = P.shift[i];
+    }
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
@@ -275,19 +280,20 @@ k_conv_halo(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 tmem_ld_wait();
                 const int c0 = g * 32;
                 float y[32];
+                const float4* pb = reinterpret_cast<const float4*>(s_par + c0);
+                const float4* ps = reinterpret_cast<const float4*>(s_par + COUT + c0);
+                const float4* pt = reinterpret_cast<const float4*>(s_par + 2 * COUT + c0);
 #pragma unroll
                 for (int k4 = 0; k4 < 8; ++k4) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.bias + c0) + k4);
-                    const float4 s4 = __ldg(reinterpret_cast<const float4*>(P.scale + c0) + k4);
-                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(P.shift + c0) + k4);
-                    const float z0 = __uint_as_float(v[4 * k4 + 0]) + b4.x;
-                    const float z1 = __uint_as_float(v[4 * k4 + 1]) + b4.y;
-                    const float z2 = __uint_as_float(v[4 * k4 + 2]) + b4.z;
-                    const float z3 = __uint_as_float(v[4 * k4 + 3]) + b4.w;
-                    y[4 * k4 + 0] = (z0 > 0.f ? z0 : 0.2f * z0) * s4.x + t4.x;
-                    y[4 * k4 + 1] = (z1 > 0.f ? z1 : 0.2f * z1) * s4.y + t4.y;
-                    y[4 * k4 + 2] = (z2 > 0.f ? z2 : 0.2f * z2) * s4.z + t4.z;
-                    y[4 * k4 + 3] = (z3 > 0.f ? z3 : 0.2f * z3) * s4.w + t4.w;
+                    const float4 b4 = pb[k4], s4 = ps[k4], t4 = pt[k4];
+                    const float2 za = add2_f32(make_float2(__uint_as_float(v[4 * k4 + 0]), __uint_as_float(v[4 * k4 + 1])), make_float2(b4.x, b4.y));
+                    const float2 zb = add2_f32(make_float2(__uint_as_float(v[4 * k4 + 2]), __uint_as_float(v[4 * k4 + 3])), make_float2(b4.z, b4.w));
+                    float2 la = mul2_f32(za, make_float2(0.2f, 0.2f)), lb = mul2_f32(zb, make_float2(0.2f, 0.2f));
+                    la.x = fmaxf(la.x, za.x); la.y = fmaxf(la.y, za.y);        // leaky(z) = max(z, 0.2 z)
+                    lb.x = fmaxf(lb.x, zb.x); lb.y = fmaxf(lb.y, zb.y);
+                    const float2 ya = fma2_f32(la, make_float2(s4.x, s4.y), make_float2(t4.x, t4.y));
+                    const float2 yb = fma2_f32(lb, make_float2(s4.z, s4.w), make_float2(t4.z, t4.w));
+                    y[4 * k4 + 0] = ya.x; y[4 * k4 + 1] = ya.y; y[4 * k4 + 2] = yb.x; y[4 * k4 + 3] = yb.y;
                 }
                 const int ch = g >> 1;
                 const int piece0 = (g & 1) * 4;

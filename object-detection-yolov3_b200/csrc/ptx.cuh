@@ -276,3 +276,26 @@ __device__ __forceinline__ void tma2_load_im2col_4d(void* dst, const CUtensorMap
         : "memory");
 }
 }}  // namespace y3::ptx
+
+// ======================================================================= packed fp32 (FADD2 / FMUL2 / FFMA2)
+namespace y3 { namespace ptx {
+__device__ __forceinline__ float2 add2_f32(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rr; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.f32x2 rr, ra, rb; mov.b64 {%0,%1}, rr;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 mul2_f32(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rr; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.f32x2 rr, ra, rb; mov.b64 {%0,%1}, rr;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 fma2_f32(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc, rr; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rr, ra, rb, rc; "
+        "mov.b64 {%0,%1}, rr;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+}}  // namespace y3::ptx

@@ -21,19 +21,6 @@ __device__ __forceinline__ uint64_t make_smem_desc_noswz(uint32_t saddr, uint32_
     return d;                                                // layout_type 0 = no swizzle (interleaved)
 }
 
-__device__ __forceinline__ float2 mul2_f32(float2 a, float2 b) {
-    float2 r;
-    asm("{.reg .b64 ra, rb, rr; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.f32x2 rr, ra, rb; mov.b64 {%0,%1}, rr;}"
-        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return r;
-}
-__device__ __forceinline__ float2 fma2_f32(float2 a, float2 b, float2 c) {
-    float2 r;
-    asm("{.reg .b64 ra, rb, rc, rr; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rr, ra, rb, rc; "
-        "mov.b64 {%0,%1}, rr;}"
-        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-    return r;
-}
 __device__ __forceinline__ void st_global_256(void* p, const uint32_t* v) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
                  "r"(v[5]), "r"(v[6]), "r"(v[7])
