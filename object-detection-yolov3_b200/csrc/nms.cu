@@ -25,6 +25,8 @@
 #include "postproc.cuh"
 
 #include <math.h>
+#include <stdlib.h>
+#include <algorithm>
 
 namespace y3 {
 
@@ -120,6 +122,79 @@ k_candidates(CandSource src, KeyLayout kl, int64_t total, float logit_floor, uin
             if (pass) {
                 const int64_t pos = (int64_t)base + __popc(m & ((1u << lane) - 1u));
                 if (pos < cap) { keys[pos] = key; vals[pos] = val; }
+            }
+        }
+    }
+}
+
+// Fused decode + threshold + compaction straight from the raw fp32 heads, organised by ROW: L = 1..32 lanes share
+// one output row (L = smallest power of two >= NC, capped at 32), so the row's address arithmetic, its objectness
+// logit and - only when needed - its box are computed once per row instead of once per (row, class), the class
+// logits of a row are read by neighbouring lanes (coalesced), and a row whose objectness logit cannot reach the
+// threshold costs ONE 4-byte load (score^2 = obj*cls <= obj).  Same exact arithmetic as k_candidates.
+__global__ void __launch_bounds__(256)
+k_candidates_heads(CandSource src, KeyLayout kl, int lanes_per_row_log2, float logit_floor, uint64_t* __restrict__ keys,
+                   uint32_t* __restrict__ vals, unsigned long long* __restrict__ counter, int64_t cap) {
+    const int lane = threadIdx.x & 31;
+    const int L = 1 << lanes_per_row_log2;
+    const int sub = lane & (L - 1);                    // this lane's first class
+    const int rows_per_warp = 32 >> lanes_per_row_log2;
+    const uint32_t rpi = (uint32_t)src.rows_per_image;
+    const uint32_t rows_total = rpi * (uint32_t)src.n_images;
+    const uint32_t warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int nc = src.nc;
+    const int iters = (nc + L - 1) >> lanes_per_row_log2;
+    const float thr = src.score_thr;
+    for (uint32_t base = warp_g * rows_per_warp; base < rows_total; base += n_warps * rows_per_warp) {
+        const uint32_t grow = base + (uint32_t)(lane >> lanes_per_row_log2);
+        const bool valid = grow < rows_total;
+        uint32_t img = 0, row = 0;
+        int sc = 0, cell = 0, a = 0;
+        const float* hp = nullptr;
+        float lo = -INFINITY;
+        if (valid) {
+            img = grow / rpi;
+            row = grow - img * rpi;
+            hp = head_row(src.dec, (int)img, (int)row, &sc, &cell, &a);
+            lo = __ldg(hp + 4);
+        }
+        const bool live = valid && (lo >= logit_floor);
+        if (!__any_sync(0xffffffffu, live)) continue;
+        const float o = live ? sigmoid_f(lo) : 0.f;
+        bool size_known = !src.filter_small, size_ok = true;
+        for (int it = 0; it < iters; ++it) {
+            const int c = sub + (it << lanes_per_row_log2);
+            bool pass = false;
+            float s = 0.f;
+            if (live && c < nc) {
+                const float lc = __ldg(hp + 5 + c);
+                if (lc >= logit_floor) {
+                    s = __fsqrt_rn(__fmul_rn(sigmoid_f(lc), o));
+                    pass = (s >= thr);
+                    if (pass && !size_known) {
+                        const float w = __fsub_rn(decode_corner(src.dec, hp, sc, cell, a, 2), decode_corner(src.dec, hp, sc, cell, a, 0));
+                        const float h = __fsub_rn(decode_corner(src.dec, hp, sc, cell, a, 3), decode_corner(src.dec, hp, sc, cell, a, 1));
+                        size_ok = (w > src.min_size) && (h > src.min_size);
+                        size_known = true;
+                    }
+                    pass = pass && size_ok;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+                unsigned long long b0 = 0;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) b0 = atomicAdd(counter, (unsigned long long)__popc(m));
+                b0 = __shfl_sync(0xffffffffu, b0, leader);
+                if (pass) {
+                    const int64_t pos = (int64_t)b0 + __popc(m & ((1u << lane) - 1u));
+                    if (pos < cap) {
+                        const uint64_t seg = (uint64_t)img * (uint64_t)nc + (uint64_t)c;
+                        keys[pos] = (seg << kl.seg_shift) | ((uint64_t)(~orderable(s)) << kl.row_bits) | (uint64_t)row;
+                        vals[pos] = grow;
+                    }
+                }
             }
         }
     }
@@ -504,7 +579,16 @@ NmsResult PostProc::run(const CandSource& src, float iou_thr) {
         const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
         if (!ev0) { Y3_CUDA(cudaEventCreate(&ev0)); Y3_CUDA(cudaEventCreate(&ev1)); }
         Y3_CUDA(cudaEventRecord(ev0, st));
-        if (total + 32 < (1ll << 32))
+        static const bool row_kernel = getenv("Y3_CAND_OLD") == nullptr;
+        if (row_kernel && src.from_heads && total + 32 < (1ll << 32)) {
+            int l2 = 0;
+            while ((1 << l2) < src.nc && l2 < 5) ++l2;
+            const int64_t rows_total = src.rows_per_image * src.n_images;
+            const int64_t warps = (rows_total + (32 >> l2) - 1) / (32 >> l2);
+            const int rblocks = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)ctx->sm_count * 16);
+            k_candidates_heads<<<rblocks, 256, 0, st>>>(src, kl, l2, logit_floor, keys[0].as<uint64_t>(), vals[0].as<uint32_t>(),
+                                                         counters.as<unsigned long long>(), cap);
+        } else if (total + 32 < (1ll << 32))
             k_candidates<uint32_t><<<blocks, 256, 0, st>>>(src, kl, total, logit_floor, keys[0].as<uint64_t>(), vals[0].as<uint32_t>(),
                                                            counters.as<unsigned long long>(), cap);
         else
