@@ -109,6 +109,16 @@ k_conv_halo(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch_dependents();
+    if (warp == 0 && lane == 0) {
+        // stationary weights: 9 taps x this CTA's half of the Cout rows; they do not depend on the previous layer,
+        // so they are requested before the grid-dependency wait
+        const uint32_t lead_w = mapa_u32(w_full, 0);
+        if (rank == 0) mbar_expect_tx(w_full, (uint32_t)(2 * C::W_BYTES));
+        for (int tap = 0; tap < 9; ++tap)
+            tma2_load_2d(w_base + tap * C::WTAP, &map_b, lead_w, tap * CIN, (int)rank * (COUT / 2));
+    }
+    griddep_wait();              // activations of the previous layer are complete and visible from here on
 
     // pair-tiles: (image pair ip, segment seg, output row h) flattened with h fastest; this pair's range
     const int Ho = P.Ho;
@@ -120,12 +130,6 @@ k_conv_halo(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (each CTA)
         if (lane == 0) {
-            {   // stationary weights: 9 taps x this CTA's half of the Cout rows
-                const uint32_t lead_w = mapa_u32(w_full, 0);
-                if (rank == 0) mbar_expect_tx(w_full, (uint32_t)(2 * C::W_BYTES));
-                for (int tap = 0; tap < 9; ++tap)
-                    tma2_load_2d(w_base + tap * C::WTAP, &map_b, lead_w, tap * CIN, (int)rank * (COUT / 2));
-            }
             int k = 0;                                  // running input-row load index (ring position)
             int it = 0;                                 // running tile index
             if (STRIDE == 2) {
@@ -357,7 +361,7 @@ static void launch_halo_t(y3_context* ctx, const ConvLaunch& L) {
     const ConvArgs& A = L.args;
     const long long total = (long long)((A.n_img + 1) / 2) * A.tiles_x * A.Ho;
     const int pairs = (int)std::min<long long>(total, (long long)(ctx->sm_count / 2) * C::CTAS_PER_SM);
-    k_conv_halo<CIN, COUT, STRIDE><<<2 * pairs, HALO_THREADS, C::SMEM, ctx->stream>>>(L.map_a, L.map_b, L.map_out, L.map_res, L.args);
+    launch_pdl(k_conv_halo<CIN, COUT, STRIDE>, 2 * pairs, HALO_THREADS, C::SMEM, ctx->stream, L.map_a, L.map_b, L.map_out, L.map_res, L.args);
     Y3_LAUNCHED(ctx);
 }
 

@@ -109,6 +109,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch_dependents();
+    griddep_wait();              // activations of the previous layer are complete and visible from here on
 
     const int rows = P.BH * P.BW;
     const int k_iters = P.taps * P.kchunks;
@@ -396,7 +398,7 @@ static void launch_t(y3_context* ctx, const ConvLaunch& L) {
         attr[ctx->device & 63] = true;
     }
     const int grid = std::min(L.args.total_tiles, ctx->sm_count * C::CTAS_PER_SM);
-    k_conv_tc<BN, BK><<<grid, CONV_THREADS, C::SMEM, ctx->stream>>>(L.map_a, L.map_a2, L.map_b, L.map_out, L.map_res, L.args);
+    launch_pdl(k_conv_tc<BN, BK>, grid, CONV_THREADS, C::SMEM, ctx->stream, L.map_a, L.map_a2, L.map_b, L.map_out, L.map_res, L.args);
     Y3_LAUNCHED(ctx);
 }
 

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
+#include <stdlib.h>
+#include <utility>
 
 namespace y3 {
 
@@ -42,6 +44,22 @@ void encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64
                       const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box, int swizzle_bytes);
 
 void launch_conv(y3_context* ctx, const ConvLaunch& L);
+
+// Optional launch with programmatic stream serialization (Y3_PDL=1): the kernel may become resident while its
+// predecessor in the stream drains; every thread executes griddepcontrol.wait before it touches activations.
+// Measured on B200 (round 1): no gain for this stack (12.88 vs 12.83 ms per 128 tiles) - the persistent CTAs hold
+// every SM until they exit, so there is nothing to overlap - hence off by default.
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
+    static const bool pdl = getenv("Y3_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    Y3_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+}
 void launch_conv2(y3_context* ctx, const ConvLaunch& L);
 bool launch_conv2h(y3_context* ctx, const ConvLaunch& L);   // half-staged variant (conv_tc2h.cu); false = not used
 void launch_conv_halo(y3_context* ctx, const ConvLaunch& L);

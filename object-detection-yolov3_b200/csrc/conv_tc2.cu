@@ -97,6 +97,8 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch_dependents();
+    griddep_wait();              // activations of the previous layer are complete and visible from here on
 
     const int rows = P.BH * P.BW;
     const int k_iters = P.taps * P.kchunks;
@@ -318,7 +320,7 @@ static void launch2_t(y3_context* ctx, const ConvLaunch& L) {
         Y3_CUDA(cudaFuncSetAttribute(k_conv_tc2<BN2, NSTG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr[ctx->device & 63] = true;
     }
-    k_conv_tc2<BN2, NSTG_><<<L.grid, CONV2_THREADS, C::SMEM, ctx->stream>>>(L.map_a, L.map_a2, L.map_b, L.map_out, L.map_res, L.args);
+    launch_pdl(k_conv_tc2<BN2, NSTG_>, L.grid, CONV2_THREADS, C::SMEM, ctx->stream, L.map_a, L.map_a2, L.map_b, L.map_out, L.map_res, L.args);
     Y3_LAUNCHED(ctx);
 }
 

@@ -111,6 +111,8 @@ k_conv_tc2h(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch_dependents();
+    griddep_wait();              // activations of the previous layer are complete and visible from here on
 
     const int rows = P.BH * P.BW;
     const int k_iters = P.taps * P.kchunks;
@@ -342,7 +344,7 @@ static void launch2h_t(y3_context* ctx, const ConvLaunch& L) {
         Y3_CUDA(cudaFuncSetAttribute(k_conv_tc2h<BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr[ctx->device & 63] = true;
     }
-    k_conv_tc2h<BN2><<<L.grid, CONV2H_THREADS, C::SMEM, ctx->stream>>>(L.map_a, L.map_a2, L.map_b, L.map_out, L.map_res, L.args);
+    launch_pdl(k_conv_tc2h<BN2>, L.grid, CONV2H_THREADS, C::SMEM, ctx->stream, L.map_a, L.map_a2, L.map_b, L.map_out, L.map_res, L.args);
     Y3_LAUNCHED(ctx);
 }
 

@@ -299,3 +299,12 @@ __device__ __forceinline__ float2 fma2_f32(float2 a, float2 b, float2 c) {
     return r;
 }
 }}  // namespace y3::ptx
+
+// ======================================================================= programmatic dependent launch
+namespace y3 { namespace ptx {
+// Blocks until the grids this grid depends on have completed and their memory is visible (no-op when the
+// kernel was launched without the programmatic-serialization attribute).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+// Lets the next grid of the stream start its prologue on SMs this grid no longer occupies.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+}}  // namespace y3::ptx
