@@ -39,8 +39,22 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef Y3_MBAR_SUSPEND_NS
+#define Y3_MBAR_SUSPEND_NS 10000
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+#if Y3_MBAR_SUSPEND_NS > 0
+    // suspend-time hint: the waiting thread sleeps in hardware until the phase completes (or the hint expires)
+    // instead of re-issuing the poll - fewer wasted issue slots while the step is power-capped
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)Y3_MBAR_SUSPEND_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
@@ -48,13 +62,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+#endif
     return ok != 0;
 }
 // Bounded wait: a broken pipeline traps (launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) {
+        if (++spins > (Y3_MBAR_SUSPEND_NS > 0 ? (1u << 18) : (1u << 22))) {
             printf("y3: mbarrier timeout block (%d,%d,%d) thread %d bar %p parity %u\n", blockIdx.x, blockIdx.y,
                    blockIdx.z, threadIdx.x, (void*)bar, parity);
             __trap();
