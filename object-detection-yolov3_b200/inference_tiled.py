@@ -21,7 +21,7 @@ import model
 from bbox_utils import compute_iou, filter_small_boxes, per_class_nms, single_class_nms  # noqa: F401
 from yolo3_b200 import infer_tiled_distributed, post_engine, tile_plan
 
-BATCH_SIZE = 64          # tiles per forward batch (declared but unused in the reference)
+BATCH_SIZE = 256         # tiles per forward batch at 512x512 (scaled down for larger tiles; declared = 1, unused, in the reference)
 EDGE_EFFECT_RANGE = 96
 # Optional extra stage, off by default because the reference has none (seams are resolved by centre ownership
 # only): greedy per-class NMS among the final boxes that straddle a tile-zone boundary.  Set the constant or
@@ -78,7 +78,8 @@ def inference_image_folder(image_folder, image_format, saved_model_filepath, out
     image_format = image_format[1:] if image_format.startswith('.') else image_format
     files = [os.path.join(image_folder, fn) for fn in os.listdir(image_folder) if fn.endswith('.{}'.format(image_format))]
     device = int(os.environ.get("LOCAL_RANK", "0")) if _distributed() else 0
-    yolo_model = model.load_saved_model(saved_model_filepath, max_batch=BATCH_SIZE, device=device)
+    max_batch = max(1, min(BATCH_SIZE, BATCH_SIZE * 512 * 512 // max(1, int(tile_size[0]) * int(tile_size[1]))))
+    yolo_model = model.load_saved_model(saved_model_filepath, max_batch=max_batch, device=device)
     os.makedirs(output_folder, exist_ok=True)
     print('Starting inference of file list')
     for i, fp in enumerate(files):
