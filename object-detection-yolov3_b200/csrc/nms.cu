@@ -49,6 +49,9 @@ __device__ __forceinline__ float from_orderable(uint32_t o) {
 struct KeyLayout {
     int row_bits, seg_shift, total_bits;
     uint64_t row_mask;
+    // score field = ~orderable(score) - score_base in score_bits bits: scores known to lie in [thr, 1] (the fused
+    // sqrt(sigmoid*sigmoid) path) need 25 bits instead of 32 => one radix pass less
+    uint32_t score_base, score_mask;
 };
 
 // IDX = uint32_t when the element count fits (the common case): 64-bit divisions are ~10x slower
@@ -109,7 +112,7 @@ k_candidates(CandSource src, KeyLayout kl, int64_t total, float logit_floor, uin
             }
             if (pass) {
                 const uint64_t seg = (uint64_t)img * src.nc + (uint64_t)c;
-                key = (seg << kl.seg_shift) | ((uint64_t)(~orderable(s)) << kl.row_bits) | (uint64_t)row;
+                key = (seg << kl.seg_shift) | ((uint64_t)(~orderable(s) - kl.score_base) << kl.row_bits) | (uint64_t)row;
                 val = (uint32_t)grow;
             }
         }
@@ -191,7 +194,7 @@ k_candidates_heads(CandSource src, KeyLayout kl, int lanes_per_row_log2, float l
                     const int64_t pos = (int64_t)b0 + __popc(m & ((1u << lane) - 1u));
                     if (pos < cap) {
                         const uint64_t seg = (uint64_t)img * (uint64_t)nc + (uint64_t)c;
-                        keys[pos] = (seg << kl.seg_shift) | ((uint64_t)(~orderable(s)) << kl.row_bits) | (uint64_t)row;
+                        keys[pos] = (seg << kl.seg_shift) | ((uint64_t)(~orderable(s) - kl.score_base) << kl.row_bits) | (uint64_t)row;
                         vals[pos] = grow;
                     }
                 }
@@ -282,11 +285,29 @@ k_rs_scan(int* __restrict__ a, int64_t n) {
 
 __global__ void __launch_bounds__(RS_THREADS)
 k_rs_scatter(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
-             uint32_t* __restrict__ vout, int64_t n, int shift, int nblocks, const int* __restrict__ hist) {
+             uint32_t* __restrict__ vout, int64_t n, int shift, int nblocks, const int* __restrict__ hist, int scanned) {
     __shared__ int s_run[256];                 // next output slot of each digit for this block
     __shared__ int s_cnt[RS_THREADS / 32][256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    s_run[threadIdx.x] = hist[(int64_t)threadIdx.x * nblocks + blockIdx.x];
+    if (scanned) {
+        s_run[threadIdx.x] = hist[(int64_t)threadIdx.x * nblocks + blockIdx.x];
+    } else {
+        // raw per-block counts: thread d derives "keys with a smaller digit" + "same digit in earlier blocks" itself
+        // (256 x nblocks ints, L2 resident) - saves the one-block scan launch of every pass
+        const int* row = hist + (int64_t)threadIdx.x * nblocks;
+        int total = 0, before = 0;
+        for (int b = 0; b < nblocks; ++b) { const int c = row[b]; total += c; if (b < (int)blockIdx.x) before += c; }
+        __shared__ int s_tot[256];
+        s_tot[threadIdx.x] = total;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {
+            const int v = (threadIdx.x >= o) ? s_tot[threadIdx.x - o] : 0;
+            __syncthreads();
+            s_tot[threadIdx.x] += v;
+            __syncthreads();
+        }
+        s_run[threadIdx.x] = s_tot[threadIdx.x] - total + before;
+    }
 #pragma unroll
     for (int w = 0; w < RS_THREADS / 32; ++w) s_cnt[w][threadIdx.x] = 0;
     __syncthreads();
@@ -395,16 +416,59 @@ __device__ __forceinline__ void chunk_resolve(ChunkSmem& S, const float4* __rest
     __syncthreads();
 }
 
+// Segments of at most 64 boxes (the many-class regime: K2 has 5120 segments of ~50 boxes): one WARP per segment,
+// two boxes per lane, the alive set is a 64-bit mask every lane keeps in step through ballots.  Same greedy order
+// and the same exact suppression test as the chunk path.
+static constexpr int NMS_SMALL = 64;
+__global__ void __launch_bounds__(256)
+k_nms_small(const float4* __restrict__ sbox, const float* __restrict__ sarea, uint8_t* __restrict__ keepf,
+            const int64_t* __restrict__ seg_off, int nseg, float thr) {
+    const int lane = threadIdx.x & 31;
+    const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int seg = warp_g; seg < nseg; seg += n_warps) {
+        const int64_t s0 = seg_off[seg];
+        const int m = (int)min((int64_t)(NMS_SMALL + 1), seg_off[seg + 1] - s0);
+        if (m <= 0 || m > NMS_SMALL) continue;
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+        float a0 = 0.f, a1 = 0.f;
+        if (lane < m) { b0 = sbox[s0 + lane]; a0 = sarea[s0 + lane]; }
+        if (lane + 32 < m) { b1 = sbox[s0 + lane + 32]; a1 = sarea[s0 + lane + 32]; }
+        unsigned long long alive = (m == 64) ? ~0ull : ((1ull << m) - 1ull);
+        unsigned long long kept = 0;
+        while (alive) {
+            const int i = __ffsll((long long)alive) - 1;
+            alive &= ~(1ull << i);
+            kept |= 1ull << i;
+            const int src = i & 31;
+            const bool hi = i >= 32;
+            float4 bi;
+            bi.x = __shfl_sync(0xffffffffu, hi ? b1.x : b0.x, src);
+            bi.y = __shfl_sync(0xffffffffu, hi ? b1.y : b0.y, src);
+            bi.z = __shfl_sync(0xffffffffu, hi ? b1.z : b0.z, src);
+            bi.w = __shfl_sync(0xffffffffu, hi ? b1.w : b0.w, src);
+            const float ai = __shfl_sync(0xffffffffu, hi ? a1 : a0, src);
+            const bool k0 = ((alive >> lane) & 1ull) && suppresses_exact(bi, ai, b0, a0, thr);
+            const bool k1 = ((alive >> (lane + 32)) & 1ull) && suppresses_exact(bi, ai, b1, a1, thr);
+            const unsigned long long dead = (unsigned long long)__ballot_sync(0xffffffffu, k0) |
+                                            ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32);
+            alive &= ~dead;
+        }
+        if ((kept >> lane) & 1ull) keepf[s0 + lane] = 1;
+        if ((kept >> (lane + 32)) & 1ull) keepf[s0 + lane + 32] = 1;
+    }
+}
+
 __global__ void __launch_bounds__(NMS_THREADS)
 k_nms_segments(const float4* __restrict__ sbox, const float* __restrict__ sarea, uint8_t* __restrict__ supp,
                uint8_t* __restrict__ keepf, const int64_t* __restrict__ seg_off, int nseg, float thr,
-               int64_t big_segment) {
+               int64_t big_segment, int64_t small_segment) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ChunkSmem& S = *reinterpret_cast<ChunkSmem*>(smem_raw);
     for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
         const int64_t s0 = seg_off[seg];
         const int64_t m = seg_off[seg + 1] - s0;
-        if (m <= 0 || m > big_segment) continue;
+        if (m <= small_segment || m > big_segment) continue;       // small ones: k_nms_small
         for (int64_t c0 = 0; c0 < m; c0 += NMS_T) {
             const int ct = (int)min((int64_t)NMS_T, m - c0);
             chunk_resolve(S, sbox, sarea, supp, s0 + c0, ct, thr);
@@ -518,7 +582,7 @@ k_scatter(const uint8_t* __restrict__ flags, int64_t n, const int* __restrict__ 
         const uint64_t key = keys[p];
         const uint64_t seg = key >> kl.seg_shift;
         o_box[q] = sbox[p];
-        o_score[q] = from_orderable(~(uint32_t)(key >> kl.row_bits));
+        o_score[q] = from_orderable(~(((uint32_t)(key >> kl.row_bits) & kl.score_mask) + kl.score_base));
         o_label[q] = (int32_t)(seg % (uint64_t)nc);
         o_img[q] = (int32_t)(seg / (uint64_t)nc);
         o_src[q] = (int32_t)(key & kl.row_mask);
@@ -554,7 +618,20 @@ NmsResult PostProc::run(const CandSource& src, float iou_thr) {
     KeyLayout kl;
     kl.row_bits = ilog2_ceil((uint64_t)src.rows_per_image);
     if (kl.row_bits == 0) kl.row_bits = 1;
-    kl.seg_shift = kl.row_bits + 32;
+    int score_bits = 32;
+    kl.score_base = 0;
+    if (src.from_heads && src.score_thr > 0.f && src.score_thr < 1.f) {
+        // host mirror of orderable(): positive floats map to bits | 0x80000000
+        uint32_t hi_bits, lo_bits;
+        const float one = 1.0f, thr = src.score_thr;
+        memcpy(&hi_bits, &one, 4); memcpy(&lo_bits, &thr, 4);
+        kl.score_base = ~(hi_bits | 0x80000000u);                       // ~orderable(1.0f): the smallest field value
+        const uint32_t span = ~(lo_bits | 0x80000000u) - kl.score_base; // ~orderable(thr) - base: the largest
+        score_bits = ilog2_ceil((uint64_t)span + 1);
+        if (score_bits < 1) score_bits = 1;
+    }
+    kl.score_mask = score_bits >= 32 ? 0xffffffffu : ((1u << score_bits) - 1u);
+    kl.seg_shift = kl.row_bits + score_bits;
     const int seg_bits = ilog2_ceil((uint64_t)nseg64 + 1);
     kl.total_bits = kl.seg_shift + seg_bits;
     kl.row_mask = (1ull << kl.row_bits) - 1ull;
@@ -617,11 +694,14 @@ NmsResult PostProc::run(const CandSource& src, float iou_thr) {
             const int dst_buf = src_buf ^ 1;
             k_rs_hist<<<nblocks, RS_THREADS, 0, st>>>(keys[src_buf].as<uint64_t>(), K, shift, nblocks, sort_tmp.as<int>());
             Y3_LAUNCHED(ctx);
-            k_rs_scan<<<1, 1024, 0, st>>>(sort_tmp.as<int>(), (int64_t)256 * nblocks);
-            Y3_LAUNCHED(ctx);
+            const int scanned = nblocks > 512 ? 1 : 0;     // few blocks: every scatter block sums the histogram itself
+            if (scanned) {
+                k_rs_scan<<<1, 1024, 0, st>>>(sort_tmp.as<int>(), (int64_t)256 * nblocks);
+                Y3_LAUNCHED(ctx);
+            }
             k_rs_scatter<<<nblocks, RS_THREADS, 0, st>>>(keys[src_buf].as<uint64_t>(), vals[src_buf].as<uint32_t>(),
                                                         keys[dst_buf].as<uint64_t>(), vals[dst_buf].as<uint32_t>(), K, shift, nblocks,
-                                                        sort_tmp.as<int>());
+                                                        sort_tmp.as<int>(), scanned);
             Y3_LAUNCHED(ctx);
             src_buf = dst_buf;
         }
@@ -654,10 +734,17 @@ NmsResult PostProc::run(const CandSource& src, float iou_thr) {
     const size_t smem = sizeof(ChunkSmem);
     static_assert(sizeof(ChunkSmem) <= 48 * 1024, "ChunkSmem must fit the default dynamic smem limit");
     if (any_small) {
+        static const bool warp_nms = getenv("Y3_NO_WARP_NMS") == nullptr;
+        if (warp_nms && nseg > 1) {
+            const int wblocks = std::min((nseg + 7) / 8, ctx->sm_count * 8);
+            k_nms_small<<<wblocks, 256, 0, st>>>(sbox.as<float4>(), sarea.as<float>(), keepf.as<uint8_t>(), seg_off.as<int64_t>(), nseg,
+                                                  iou_thr);
+            Y3_LAUNCHED(ctx);
+        }
         const int blocks = std::min(nseg, ctx->sm_count * 4);
         k_nms_segments<<<blocks, NMS_THREADS, smem, st>>>(sbox.as<float4>(), sarea.as<float>(), supp.as<uint8_t>(),
                                                           keepf.as<uint8_t>(), seg_off.as<int64_t>(), nseg, iou_thr,
-                                                          BIG_SEGMENT);
+                                                          BIG_SEGMENT, (warp_nms && nseg > 1) ? (int64_t)NMS_SMALL : 0);
         Y3_LAUNCHED(ctx);
     }
     if (any_big) {

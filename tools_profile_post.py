@@ -1,0 +1,22 @@
+"""K2 (416x416x3, batch 64, NC=80) detect() once warm, once measured - run under
+`ncu --metrics gpu__time_duration.sum` to list the decode / sort / NMS launches (measurement helper)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "object-detection-yolov3_b200"))
+import bench  # noqa: E402
+from yolo3_b200 import Engine, weights  # noqa: E402
+
+e2 = Engine((416, 416, 3), 80, bench.ANCHORS, max_batch=64)
+w2 = weights.random_init(3, 80, 3, seed=0, randomize_bn=True)
+e2.load_weights(w2)
+x2 = np.random.default_rng(1).standard_normal((64, 3, 416, 416)).astype(np.float32)
+bench.calibrate_heads(e2, w2, x2[:8], pass_frac=0.002, nc=80, interior=False)
+e2.detect(x2, bench.MIN_BOX, bench.IOU_THR, bench.SCORE_THR)
+print("MEASURED CALL")
+e2.detect(x2, bench.MIN_BOX, bench.IOU_THR, bench.SCORE_THR)
+print(e2.timings())
