@@ -416,10 +416,50 @@ __device__ __forceinline__ void chunk_resolve(ChunkSmem& S, const float4* __rest
     __syncthreads();
 }
 
-// Segments of at most 64 boxes (the many-class regime: K2 has 5120 segments of ~50 boxes): one WARP per segment,
-// two boxes per lane, the alive set is a 64-bit mask every lane keeps in step through ballots.  Same greedy order
-// and the same exact suppression test as the chunk path.
-static constexpr int NMS_SMALL = 64;
+// Segments of at most 256 boxes (the many-class regime: K2 has 5120 segments of ~50 boxes): one WARP per segment,
+// PL boxes per lane (box j lives in slot j / 32 of lane j % 32), the alive set is PL 32-bit masks that every lane keeps
+// in step through ballots.  Same greedy order and the same exact suppression test as the chunk path.
+static constexpr int NMS_SMALL = 256;
+
+template <int PL>
+__device__ __forceinline__ void warp_nms(const float4* __restrict__ sbox, const float* __restrict__ sarea,
+                                         uint8_t* __restrict__ keepf, int64_t s0, int m, float thr, int lane) {
+    float4 b[PL];
+    float a[PL];
+    uint32_t alive[PL], kept[PL];
+#pragma unroll
+    for (int k = 0; k < PL; ++k) {
+        const int j = k * 32 + lane;
+        const bool valid = j < m;
+        b[k] = valid ? sbox[s0 + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        a[k] = valid ? sarea[s0 + j] : 0.f;
+        alive[k] = __ballot_sync(0xffffffffu, valid);
+        kept[k] = 0;
+    }
+#pragma unroll
+    for (int k0 = 0; k0 < PL; ++k0) {
+        while (alive[k0]) {
+            const int src = __ffs((int)alive[k0]) - 1;
+            alive[k0] &= ~(1u << src);
+            kept[k0] |= 1u << src;
+            float4 bi;
+            bi.x = __shfl_sync(0xffffffffu, b[k0].x, src);
+            bi.y = __shfl_sync(0xffffffffu, b[k0].y, src);
+            bi.z = __shfl_sync(0xffffffffu, b[k0].z, src);
+            bi.w = __shfl_sync(0xffffffffu, b[k0].w, src);
+            const float ai = __shfl_sync(0xffffffffu, a[k0], src);
+#pragma unroll
+            for (int k = k0; k < PL; ++k) {
+                const bool kill = ((alive[k] >> lane) & 1u) && suppresses_exact(bi, ai, b[k], a[k], thr);
+                alive[k] &= ~__ballot_sync(0xffffffffu, kill);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < PL; ++k)
+        if ((kept[k] >> lane) & 1u) keepf[s0 + k * 32 + lane] = 1;
+}
+
 __global__ void __launch_bounds__(256)
 k_nms_small(const float4* __restrict__ sbox, const float* __restrict__ sarea, uint8_t* __restrict__ keepf,
             const int64_t* __restrict__ seg_off, int nseg, float thr) {
@@ -430,32 +470,9 @@ k_nms_small(const float4* __restrict__ sbox, const float* __restrict__ sarea, ui
         const int64_t s0 = seg_off[seg];
         const int m = (int)min((int64_t)(NMS_SMALL + 1), seg_off[seg + 1] - s0);
         if (m <= 0 || m > NMS_SMALL) continue;
-        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-        float a0 = 0.f, a1 = 0.f;
-        if (lane < m) { b0 = sbox[s0 + lane]; a0 = sarea[s0 + lane]; }
-        if (lane + 32 < m) { b1 = sbox[s0 + lane + 32]; a1 = sarea[s0 + lane + 32]; }
-        unsigned long long alive = (m == 64) ? ~0ull : ((1ull << m) - 1ull);
-        unsigned long long kept = 0;
-        while (alive) {
-            const int i = __ffsll((long long)alive) - 1;
-            alive &= ~(1ull << i);
-            kept |= 1ull << i;
-            const int src = i & 31;
-            const bool hi = i >= 32;
-            float4 bi;
-            bi.x = __shfl_sync(0xffffffffu, hi ? b1.x : b0.x, src);
-            bi.y = __shfl_sync(0xffffffffu, hi ? b1.y : b0.y, src);
-            bi.z = __shfl_sync(0xffffffffu, hi ? b1.z : b0.z, src);
-            bi.w = __shfl_sync(0xffffffffu, hi ? b1.w : b0.w, src);
-            const float ai = __shfl_sync(0xffffffffu, hi ? a1 : a0, src);
-            const bool k0 = ((alive >> lane) & 1ull) && suppresses_exact(bi, ai, b0, a0, thr);
-            const bool k1 = ((alive >> (lane + 32)) & 1ull) && suppresses_exact(bi, ai, b1, a1, thr);
-            const unsigned long long dead = (unsigned long long)__ballot_sync(0xffffffffu, k0) |
-                                            ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32);
-            alive &= ~dead;
-        }
-        if ((kept >> lane) & 1ull) keepf[s0 + lane] = 1;
-        if ((kept >> (lane + 32)) & 1ull) keepf[s0 + lane + 32] = 1;
+        if (m <= 64) warp_nms<2>(sbox, sarea, keepf, s0, m, thr, lane);
+        else if (m <= 128) warp_nms<4>(sbox, sarea, keepf, s0, m, thr, lane);
+        else warp_nms<8>(sbox, sarea, keepf, s0, m, thr, lane);
     }
 }
 
@@ -736,7 +753,7 @@ NmsResult PostProc::run(const CandSource& src, float iou_thr) {
     if (any_small) {
         static const bool warp_nms = getenv("Y3_NO_WARP_NMS") == nullptr;
         if (warp_nms && nseg > 1) {
-            const int wblocks = std::min((nseg + 7) / 8, ctx->sm_count * 8);
+            const int wblocks = std::min((nseg + 7) / 8, ctx->sm_count * 6);
             k_nms_small<<<wblocks, 256, 0, st>>>(sbox.as<float4>(), sarea.as<float>(), keepf.as<uint8_t>(), seg_off.as<int64_t>(), nseg,
                                                   iou_thr);
             Y3_LAUNCHED(ctx);
