@@ -63,6 +63,9 @@ inline void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t sme
 void launch_conv2(y3_context* ctx, const ConvLaunch& L);
 bool launch_conv2h(y3_context* ctx, const ConvLaunch& L);   // half-staged variant (conv_tc2h.cu); false = not used
 void launch_conv_halo(y3_context* ctx, const ConvLaunch& L);
+// stem (1 image channel) + conv2d_1 fused (conv_stem1.cu); L = conv2d_1's halo-form launch
+void launch_stem_conv1(y3_context* ctx, const ConvLaunch& L, const float* in, const float* stem_w_host, const float* stem_bias_host,
+                       const float* stem_scale_host, const float* stem_shift_host, int H, int W);
 bool halo_supported(int cin, int cout_pad);
 
 }  // namespace y3

@@ -248,6 +248,12 @@ void Net::build() {
         if (op.kind != Op::STEM) make_launches(op);
     }
     boxes.reserve((size_t)maxB * rows_per_image * (5 + nc) * 4);
+    // stem + conv2d_1 as one kernel: the 32-channel full-resolution activation never leaves the SM.  Needs the
+    // halo-form stride-2 launch of conv2d_1; off when every layer output must exist (per-layer debug tests).
+    fuse_stem_conv1 = C == 1 && !no_reuse && getenv("Y3_NO_STEM_FUSE") == nullptr && ops.size() > 1 &&
+                      ops[0].kind == Op::STEM && ops[1].kind == Op::CONV && ops[1].launches.size() == 1 &&
+                      ops[1].launches[0].halo && ops[1].stride == 2 && ops[1].cin == 32 && ops[1].cout_pad == 64 &&
+                      ops[1].in.t == ops[0].out.t;
 }
 
 static void pick_patch(int ho, int wo, int* bh, int* bw) {
@@ -609,6 +615,14 @@ void Net::load(int n, const char* const* names, DLManagedTensor* const* tensors_
         }
     }
     Y3_CUDA(cudaStreamSynchronize(st));
+    if (fuse_stem_conv1 && loaded) {
+        const Op& s0 = ops[0];
+        stem_host.resize(288 + 96);
+        Y3_CUDA(cudaMemcpy(stem_host.data(), s0.w.p, 288 * 4, cudaMemcpyDeviceToHost));
+        Y3_CUDA(cudaMemcpy(stem_host.data() + 288, s0.bias.p, 32 * 4, cudaMemcpyDeviceToHost));
+        Y3_CUDA(cudaMemcpy(stem_host.data() + 320, s0.scale.p, 32 * 4, cudaMemcpyDeviceToHost));
+        Y3_CUDA(cudaMemcpy(stem_host.data() + 352, s0.shift.p, 32 * 4, cudaMemcpyDeviceToHost));
+    }
     // ownership: the tensors are released only when the whole call succeeded (on failure the
     // caller still owns them, so a DLPack capsule's own destructor stays valid)
     for (int i = 0; i < n; ++i)
@@ -619,7 +633,16 @@ void Net::load(int n, const char* const* names, DLManagedTensor* const* tensors_
 void Net::forward(const float* in_dev, int b, int head_set) {
     Y3_CHECK(loaded, Y3_ERR_STATE, "weights not (completely) loaded - missing %s", missing.c_str());
     Y3_CHECK(b >= 1 && b <= maxB, Y3_ERR_INVALID, "batch %d outside 1..%d", b, maxB);
-    for (Op& op : ops) {
+    for (size_t oi = 0; oi < ops.size(); ++oi) {
+        Op& op = ops[oi];
+        if (fuse_stem_conv1 && oi == 0) {
+            Op& c1 = ops[1];
+            if (cur_batch != b) set_batch(c1, b);
+            launch_stem_conv1(ctx, c1.launches[0], in_dev, stem_host.data(), stem_host.data() + 288, stem_host.data() + 320,
+                              stem_host.data() + 352, H, W);
+            ++oi;
+            continue;
+        }
         if (op.kind == Op::STEM) {
             launch_stem(ctx, in_dev, reinterpret_cast<__nv_bfloat16*>(tensors[op.out.t].ptr), op.w.as<float>(),
                         op.bias.as<float>(), op.scale.as<float>(), op.shift.as<float>(), b, H, W, C);
@@ -656,10 +679,17 @@ std::string Net::profile(int b, int iters) {
     cudaEvent_t e0, e1;
     Y3_CUDA(cudaEventCreate(&e0)); Y3_CUDA(cudaEventCreate(&e1));
     stage.reserve((size_t)b * C * H * W * 4);
-    for (Op& op : ops) {
+    for (size_t oi = 0; oi < ops.size(); ++oi) {
+        Op& op = ops[oi];
+        const bool fused01 = fuse_stem_conv1 && oi == 0;          // reported as one row under the stem's name
+        if (fuse_stem_conv1 && oi == 1) continue;
+        if (fused01) set_batch(ops[1], b);
         if (op.kind != Op::STEM) set_batch(op, b);
         auto run = [&]() {
-            if (op.kind == Op::STEM)
+            if (fused01)
+                launch_stem_conv1(ctx, ops[1].launches[0], stage.as<float>(), stem_host.data(), stem_host.data() + 288,
+                                  stem_host.data() + 320, stem_host.data() + 352, H, W);
+            else if (op.kind == Op::STEM)
                 launch_stem(ctx, stage.as<float>(), reinterpret_cast<__nv_bfloat16*>(tensors[op.out.t].ptr), op.w.as<float>(),
                             op.bias.as<float>(), op.scale.as<float>(), op.shift.as<float>(), b, H, W, C);
             else
@@ -678,11 +708,13 @@ std::string Net::profile(int b, int iters) {
         else { oh = tensors[op.out.t].h; ow = tensors[op.out.t].w; }
         const int taps = op.kind == Op::CONVT ? 4 : op.k * op.k;
         const double mpix = (double)b * (op.kind == Op::CONVT ? oh * ow / 4 : oh * ow);
-        const double flops = 2.0 * mpix * op.cout * taps * op.cin;
+        double flops = 2.0 * mpix * op.cout * taps * op.cin;
+        if (fused01) flops += 2.0 * b * (H / 2) * (W / 2) * ops[1].cout * 9 * ops[1].cin;
         const double in_px = op.kind == Op::STEM ? (double)b * H * W : (double)b * tensors[op.in.t].h * tensors[op.in.t].w;
         double bytes = in_px * op.cin * (op.kind == Op::STEM ? 4 : 2) + (double)b * oh * ow * op.cout * (op.kind == Op::DET ? 4 : 2)
                        + (double)op.cout * taps * op.cin * 2;
         if (op.res_t >= 0) bytes += (double)b * oh * ow * op.cout * 2;
+        if (fused01) bytes = (double)b * H * W * 4 + (double)b * (H / 2) * (W / 2) * ops[1].cout * 2;   // image in, conv2d_1 out
         const char* kind = op.kind == Op::STEM ? "stem" : op.kind == Op::CONV ? "conv" : op.kind == Op::DET ? "det" : op.kind == Op::UPCONV ? "upcnv" : "convt";
         int bh = 0, bw = 0, bn = 0, bk = 0, tiles = 0;
         if (!op.launches.empty()) {
@@ -690,7 +722,7 @@ std::string Net::profile(int b, int iters) {
             bh = L.args.BH; bw = L.args.BW; bn = L.bn; bk = L.bk; tiles = L.args.total_tiles * (int)op.launches.size();
         }
         char line[512];
-        snprintf(line, sizeof(line), "%s,%s,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.1f,%.1f\n", op.name.c_str(), kind, op.k, op.stride,
+        snprintf(line, sizeof(line), "%s,%s,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.1f,%.1f\n", fused01 ? "conv2d+conv2d_1" : op.name.c_str(), kind, op.k, op.stride,
                  op.cin, op.cout, oh, ow, bh, bw, bn, bk, tiles, ms, flops / (ms * 1e-3) / 1e12, bytes / (ms * 1e-3) / 1e9);
         out += line;
     }

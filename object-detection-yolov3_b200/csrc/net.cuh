@@ -61,6 +61,8 @@ struct Net {
     DevBuf boxes;                 // decoded [B, N, 5+NC] fp32
     DevBuf stage;
     bool loaded = false;
+    bool fuse_stem_conv1 = false;   // ops[0] + ops[1] run as one kernel (conv_stem1.cu): 1-channel images only
+    std::vector<float> stem_host;   // stem weights [9][32] | bias | scale | shift on the host (kernel parameters of the fused kernel)
     std::string missing = "all layers";
     int cur_batch = -1;
     int n_conv = 0, n_bn = 0, n_convt = 0;
