@@ -57,7 +57,10 @@ TAIL_NOTE = ("bf16 storage of the fm3 tail: the all-ones upsample makes the last
 @pytest.mark.parametrize("cfg", [((416, 416, 3), 80, None, 1), ((512, 512, 1), 1, None, 2),
                                  pytest.param(((512, 512, 1), 1, [(64, 384), (384, 64)], 1),
                                               marks=pytest.mark.xfail(reason=TAIL_NOTE, strict=False)),
-                                 ((608, 608, 3), 80, None, 1)])
+                                 ((608, 608, 3), 80, None, 1),
+                                 # 1-channel, not a multiple of 256 wide, odd batch: partial row segments and an idle image slot
+                                 # in the fused stem + conv2d_1 kernel and the halo kernels
+                                 ((352, 608, 1), 2, None, 3)])
 def test_heads_vs_oracle(cfg):
     img_size, nc, anchors, B = cfg
     eng, ora = make(img_size, nc, anchors, max_batch=B)
