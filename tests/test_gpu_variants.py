@@ -1,0 +1,27 @@
+"""The kernel variants that are kept behind A/B switches must stay correct: each switch is
+exercised in a subprocess and held to the same head tolerance as the default path."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+HEAD_TOL = 2e-2
+
+VARIANTS = [{}, {"Y3_NO_HALO": "1"}, {"Y3_NO_WS2": "1"}, {"Y3_NO_STEM_FUSE": "1"}, {"Y3_NO_STEM_FUSE": "1", "Y3_STEM_FP32": "1"},
+            {"Y3_DISABLE_2CTA": "1"}, {"Y3_CONV2_OLD": "1"}, {"Y3_NO_IM2COL": "1", "Y3_NO_HALO": "1"}, {"Y3_NO_UPFUSE": "1"},
+            {"Y3_PDL": "1"}]
+
+
+@pytest.mark.parametrize("env", VARIANTS, ids=lambda e: "+".join(sorted(e)) or "default")
+def test_variant_heads(env):
+    p = subprocess.run([sys.executable, os.path.join(HERE, "variant_heads.py")], env=dict(os.environ, **env),
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT ")][-1]
+    errs = json.loads(line[len("RESULT "):])
+    print(env, errs)
+    assert all(max(v) <= HEAD_TOL for v in errs.values()), errs
