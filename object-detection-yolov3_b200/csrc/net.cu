@@ -291,7 +291,13 @@ void Net::make_launches(Op& op) {
     }
     static const bool use_halo = getenv("Y3_NO_HALO") == nullptr;
     static const bool use_ws2 = getenv("Y3_NO_WS2") == nullptr;
-    if (use_halo && op.kind == Op::CONV && op.k == 3 && (op.stride == 1 || use_ws2) && op.cout == op.cout_pad && halo_supported(cin, op.cout_pad)) {
+    // a tile of the row-ring kernels is (part of) one output row: rows that fill their last 128-pixel segment badly
+    // waste MMA rows.  Measured at 608x608 (152-pixel rows, 59 % efficiency): the stride-1 halo kernel still wins
+    // (0.166 vs 0.174 ms), the stride-2 weights-stationary one loses to the flat im2col kernel (0.205 vs 0.164 ms).
+    const int wo_halo = ti.w / op.stride;
+    const double seg_eff = (double)wo_halo / (128.0 * ((wo_halo + 127) / 128));
+    const bool ws2_ok = use_ws2 && seg_eff >= 0.75;
+    if (use_halo && op.kind == Op::CONV && op.k == 3 && (op.stride == 1 || ws2_ok) && op.cout == op.cout_pad && halo_supported(cin, op.cout_pad)) {
         // shallow 3x3 layers: weights-stationary halo-row kernel (conv_halo.cu)
         ConvLaunch L;
         memset(&L, 0, sizeof(L));
