@@ -161,6 +161,11 @@ y3_status y3_tiles_normalized(y3_handle h, const void* img, y3_dtype dtype, y3_m
                               int32_t tile_h, int32_t tile_w, int32_t edge_range,
                               int64_t first, int64_t count, float* out, y3_mem out_mem);
 
+/* replaces: imagereader.zscore_normalize (imagereader.py:34-46) on an array of ANY shape (no multiple-of-32
+ * rule): out[i] = (x[i] - mean) / std with the population std over all n elements, x - mean when std <= 1.
+ * data: n elements of `dtype` (host|device); out: n fp32 (host|device). */
+y3_status y3_zscore(y3_handle h, const void* data, y3_dtype dtype, y3_mem data_mem, int64_t n, float* out, y3_mem out_mem);
+
 /* replaces: the post-network part of inference_image_tiled (inference_tiled.py:218-310) with the
  * decoded boxes of every tile supplied by the caller - dets [count, N, 5+nc] fp32 (host|device):
  * filter_small_boxes -> per_class_nms -> ghost-band ownership -> origin add -> np.round ->

@@ -539,6 +539,30 @@ y3_status y3_tiles_normalized(y3_handle h, const void* img, y3_dtype dt, y3_mem 
     Y3_API_END(h)
 }
 
+y3_status y3_zscore(y3_handle h, const void* data, y3_dtype dt, y3_mem data_mem, int64_t n, float* out, y3_mem out_mem) {
+    Y3_API_BEGIN(h)
+    Y3_CHECK(data && out && n > 0 && n < (1ll << 31), Y3_ERR_INVALID, "bad arguments (1 <= n < 2^31)");
+    Tiler* T = tiler_of(h);
+    // one "tile" of th x tw = n elements, th = the largest power of two <= 4096 dividing n (rows spread over the CTAs)
+    int th = 1;
+    while (th < 4096 && n % (2 * th) == 0) th *= 2;
+    const int tw = (int)(n / th);
+    TileGeo g{};
+    g.y0 = 0; g.y1 = th; g.x0 = 0; g.x1 = tw; g.pre_y = 0; g.pre_x = 0; g.rec_x = 0; g.rec_y = 0;
+    const size_t in_bytes = (size_t)n * dtype_size(dt);
+    const void* d_in = to_device(h, data, data_mem, in_bytes, T->img);
+    T->geo.reserve(sizeof(TileGeo));
+    Y3_CUDA(cudaMemcpyAsync(T->geo.p, &g, sizeof(TileGeo), cudaMemcpyHostToDevice, h->stream));
+    Y3_CUDA(cudaStreamSynchronize(h->stream));     // g is a host temporary
+    const size_t bytes = (size_t)n * 4;
+    float* dst = out_mem == Y3_MEM_DEVICE ? out : (T->tiles.reserve(bytes), T->tiles.as<float>());
+    T->sums.reserve(16);
+    launch_tile_norm(h, d_in, dt, 0, tw, 1, T->geo.as<TileGeo>(), 1, th, tw, dst, nullptr, T->sums.as<double>());
+    if (out_mem != Y3_MEM_DEVICE) from_device(h, out, out_mem, dst, bytes);
+    Y3_CUDA(cudaStreamSynchronize(h->stream));
+    Y3_API_END(h)
+}
+
 y3_status y3_tiles_raw(y3_handle h, const void* img, y3_dtype dt, y3_mem img_mem, int64_t H, int64_t W, int32_t C,
                        int32_t th, int32_t tw, int32_t edge, int64_t first, int64_t count, void* out, y3_mem out_mem) {
     Y3_API_BEGIN(h)

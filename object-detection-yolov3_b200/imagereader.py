@@ -6,19 +6,9 @@ from yolo3_b200 import post_engine
 
 
 def zscore_normalize(image_data):
-    """(x - mean) / std with population std over the whole array; x - mean when std <= 1.0.
-    Runs on the GPU as a single full-size tile (same kernel as the tiled front-end)."""
-    a = np.asarray(image_data)
-    if a.dtype not in (np.uint8, np.uint16, np.int32, np.float32):
-        a = a.astype(np.float32)
-    shape = a.shape
-    hwc = a.reshape(shape[0], -1, 1) if a.ndim != 3 else a
-    h, w, c = hwc.shape
-    ph, pw = (-h) % 32, (-w) % 32
-    if ph or pw:
-        raise ValueError("zscore_normalize on the GPU needs H and W to be multiples of 32 (got %dx%d)" % (h, w))
-    out = post_engine().tiles_normalized(np.ascontiguousarray(hwc), (h, w), 0)[0]     # [C,H,W]
-    return np.ascontiguousarray(out.transpose(1, 2, 0)).reshape(shape)
+    """(x - mean) / std with the population std over the whole array; x - mean when std <= 1.0 (any shape).
+    Runs on the GPU (y3_zscore: the statistics / normalisation kernels of the tiled front-end)."""
+    return post_engine().zscore(np.asarray(image_data))
 
 
 def imread(fp):
@@ -34,3 +24,22 @@ def imread(fp):
         pass
     from PIL import Image
     return np.asarray(Image.open(fp))
+
+
+def imwrite(img, fp):
+    """skimage.io.imsave replacement (imagereader.py:52-53)."""
+    img = np.asarray(img)
+    try:
+        import cv2
+        out = img[:, :, [2, 1, 0] + list(range(3, img.shape[2]))] if img.ndim == 3 and img.shape[2] >= 3 else img
+        if cv2.imwrite(fp, out):
+            return
+    except ImportError:
+        pass
+    from PIL import Image
+    Image.fromarray(img).save(fp)
+
+
+def format_image(image_data):
+    """HWC -> CHW (imagereader.py:56-59)."""
+    return np.transpose(image_data, [2, 0, 1])

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "y3_tile_plan": (c_int64, [c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int64]),
     "y3_tiles_normalized": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int64, c_int32, c_int32,
                                       c_int32, c_int32, c_int64, c_int64, c_void_p, c_int32]),
+    "y3_zscore": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_void_p, c_int32]),
     "y3_tiles_raw": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int64, c_int32, c_int32,
                                c_int32, c_int32, c_int64, c_int64, c_void_p, c_int32]),
     "y3_stitch_tiles": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int64, c_int64, c_int32, c_int32,

@@ -173,6 +173,16 @@ class Engine:
                                            int(tile_size[1]), int(edge_range), first, count, out.ctypes.data, MEM_HOST), self.h)
         return out
 
+    def zscore(self, data):
+        """imagereader.zscore_normalize for an array of any shape -> float32 array of the same shape."""
+        a = np.ascontiguousarray(data)
+        if a.dtype not in _DTYPES:
+            a = a.astype(np.float32)
+        out = np.empty(a.shape, np.float32)
+        if a.size:
+            check(self.lib.y3_zscore(self.h, a.ctypes.data, _DTYPES[a.dtype], MEM_HOST, a.size, out.ctypes.data, MEM_HOST), self.h)
+        return out
+
     def tiles_raw(self, img, tile_size, edge_range=96, first=0, count=None):
         H, W, C = (int(v) for v in img.shape)
         total = tile_count(H, W, tile_size, edge_range)

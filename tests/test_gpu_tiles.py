@@ -57,3 +57,19 @@ def test_stitch_pipeline_golden(post, golden, tag):
         a = post.stitch_tiles(dets[:half], (h, w), tile, minbox, edge, first=0)
         b = post.stitch_tiles(dets[half:], (h, w), tile, minbox, edge, first=half)
         assert np.array_equal(np.concatenate([a, b]), g[tag + "_pred"])
+
+
+@pytest.mark.parametrize("shape,dt", [((37, 53, 3), np.uint8), ((416, 416, 3), np.float32), ((1000, 1001), np.uint16),
+                                       ((7,), np.int32), ((64, 64, 1), np.uint16)])
+def test_zscore_normalize_any_shape(shape, dt):
+    """imagereader.zscore_normalize (imagereader.py:34-46) has no multiple-of-32 rule: y3_zscore"""
+    import imagereader
+    rng = np.random.default_rng(len(shape) * 11 + shape[0])
+    a = (rng.standard_normal(shape) * 40 + 100).astype(dt) if dt != np.uint16 else rng.integers(0, 65535, shape).astype(dt)
+    got = imagereader.zscore_normalize(a)
+    want = tl.zscore(a)
+    assert got.dtype == np.float32 and got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=3e-6, atol=3e-6)
+    # std <= 1 branch
+    flat = np.full(shape, 5, dt)
+    np.testing.assert_allclose(imagereader.zscore_normalize(flat), 0.0, atol=1e-6)
