@@ -355,18 +355,22 @@ struct ChunkSmem {
     int nk;
 };
 
+// idx (optional, shared memory): the chunk is the gathered boxes sbox[base + idx[j]] (all alive) instead of the
+// contiguous run sbox[base + j]
 __device__ __forceinline__ void chunk_resolve(ChunkSmem& S, const float4* __restrict__ sbox,
                                               const float* __restrict__ sarea,
-                                              const uint8_t* __restrict__ supp, int64_t base, int ct, float thr) {
+                                              const uint8_t* __restrict__ supp, int64_t base, int ct, float thr,
+                                              const int* idx = nullptr) {
     const int tid = threadIdx.x;
     // load + dead bits (already suppressed by earlier chunks, or past the end)
     uint32_t* dead32 = reinterpret_cast<uint32_t*>(S.dead);
     for (int j = tid; j < NMS_T; j += NMS_THREADS) {
         bool dead = true;
         if (j < ct) {
-            S.box[j] = sbox[base + j];
-            S.area[j] = sarea[base + j];
-            dead = supp[base + j] != 0;
+            const int64_t e = base + (idx ? idx[j] : j);
+            S.box[j] = sbox[e];
+            S.area[j] = sarea[e];
+            dead = idx ? false : (supp[e] != 0);
         }
         const unsigned b = __ballot_sync(0xffffffffu, dead);
         if ((tid & 31) == 0) dead32[j >> 5] = b;
@@ -536,6 +540,89 @@ k_nms_apply(const float4* __restrict__ sbox, const float* __restrict__ sarea, ui
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t j = first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < last; j += stride) {
+        if (supp[j]) continue;
+        const float4 bj = sbox[j];
+        const float aj = sarea[j];
+        for (int t = 0; t < nk; ++t) {
+            if (suppresses_exact(s_box[t], s_area[t], bj, aj, thr)) { supp[j] = 1; break; }
+        }
+    }
+}
+
+// Very large segments, cursor form: instead of fixed 512-box windows (most of whose boxes are long dead deep into
+// the segment), every step gathers the NEXT 512 still-alive boxes after a device-side cursor, resolves them, and
+// applies their kept boxes to everything after the new cursor.  Same greedy order, ~5x fewer steps at 200 k boxes.
+struct BigState {
+    long long cursor;      // first segment-relative position not yet gathered
+    int knum;              // kept boxes published by the last resolve
+    int done;              // cursor reached the end of the segment
+};
+
+__global__ void __launch_bounds__(NMS_THREADS)
+k_nms_resolve_next(const float4* __restrict__ sbox, const float* __restrict__ sarea, const uint8_t* __restrict__ supp,
+                   uint8_t* __restrict__ keepf, int64_t s0, int64_t m, float thr, float4* __restrict__ kbox,
+                   float* __restrict__ karea, BigState* __restrict__ st) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ChunkSmem& S = *reinterpret_cast<ChunkSmem*>(smem_raw);
+    __shared__ int s_idx[NMS_T];
+    __shared__ int s_wcount[NMS_THREADS / 32];
+    __shared__ int s_n;
+    __shared__ long long s_pos;
+    if (threadIdx.x == 0) { s_n = 0; s_pos = st->cursor; }
+    __syncthreads();
+    if (s_pos >= m) {
+        if (threadIdx.x == 0) { st->knum = 0; st->done = 1; }
+        return;
+    }
+    // gather: windows of NMS_THREADS positions, ordered compaction of the alive ones into s_idx
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    while (true) {
+        const long long pos = s_pos;
+        const int have = s_n;
+        if (pos >= m || have >= NMS_T) break;
+        const long long p = pos + threadIdx.x;
+        const bool alive = p < m && supp[s0 + p] == 0;
+        const unsigned b = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) s_wcount[wid] = __popc(b);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < NMS_THREADS / 32; ++w) { const int c = s_wcount[w]; if (w < wid) before += c; total += c; }
+        const int rank = have + before + __popc(b & ((1u << lane) - 1u));
+        if (alive && rank < NMS_T) s_idx[rank] = (int)p;
+        // positions consumed: the whole window if everything fitted, else up to the alive box that took the last slot
+        __syncthreads();
+        if (have + total <= NMS_T) {
+            if (threadIdx.x == 0) { s_n = have + total; s_pos = min(pos + (long long)NMS_THREADS, (long long)m); }
+        } else {
+            if (alive && rank == NMS_T - 1) { s_n = NMS_T; s_pos = p + 1; }
+        }
+        __syncthreads();
+    }
+    const int ct = s_n;
+    if (ct > 0) chunk_resolve(S, sbox, sarea, supp, s0, ct, thr, s_idx);
+    const int nk = ct > 0 ? S.nk : 0;
+    for (int t = threadIdx.x; t < nk; t += NMS_THREADS) {
+        const int k = S.klist[t];
+        keepf[s0 + s_idx[k]] = 1;
+        kbox[t] = S.box[k];
+        karea[t] = S.area[k];
+    }
+    if (threadIdx.x == 0) { st->knum = nk; st->cursor = s_pos; st->done = (s_pos >= m) ? 1 : 0; }
+}
+
+__global__ void __launch_bounds__(256)
+k_nms_apply_from(const float4* __restrict__ sbox, const float* __restrict__ sarea, uint8_t* __restrict__ supp,
+                 int64_t s0, int64_t m, float thr, const float4* __restrict__ kbox, const float* __restrict__ karea,
+                 const BigState* __restrict__ st) {
+    __shared__ float4 s_box[NMS_T];
+    __shared__ float s_area[NMS_T];
+    const int nk = st->knum;
+    const long long first = st->cursor;
+    if (nk == 0 || first >= m) return;
+    for (int t = threadIdx.x; t < nk; t += blockDim.x) { s_box[t] = kbox[t]; s_area[t] = karea[t]; }
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = s0 + first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < s0 + m; j += stride) {
         if (supp[j]) continue;
         const float4 bj = sbox[j];
         const float aj = sarea[j];
@@ -765,13 +852,37 @@ NmsResult PostProc::run(const CandSource& src, float iou_thr) {
         Y3_LAUNCHED(ctx);
     }
     if (any_big) {
-        kbuf.reserve((size_t)NMS_T * 20 + 16);
+        kbuf.reserve((size_t)NMS_T * 20 + 16 + 64);
         float4* kbox = kbuf.as<float4>();
         float* karea = reinterpret_cast<float*>(kbuf.as<unsigned char>() + (size_t)NMS_T * 16);
         int* knum = reinterpret_cast<int*>(kbuf.as<unsigned char>() + (size_t)NMS_T * 20);
         for (int s = 0; s < nseg; ++s) {
             const int64_t s0 = h_off[s], m = h_off[s + 1] - h_off[s];
             if (m <= BIG_SEGMENT) continue;
+            static const bool cursor_form = getenv("Y3_NMS_FIXED_CHUNKS") == nullptr;
+            if (cursor_form) {
+                BigState* bs = reinterpret_cast<BigState*>(kbuf.as<unsigned char>() + (size_t)NMS_T * 20 + 16);
+                Y3_CUDA(cudaMemsetAsync(bs, 0, sizeof(BigState), st));
+                BigState* h_bs = reinterpret_cast<BigState*>(host_small.as<unsigned char>() + 32);
+                const int blocks = (int)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 8);
+                const int64_t max_steps = (m + NMS_T - 1) / NMS_T;          // every step consumes >= NMS_T positions or ends
+                for (int64_t step = 0; step < max_steps;) {
+                    const int burst = (int)std::min<int64_t>(16, max_steps - step);
+                    for (int b = 0; b < burst; ++b) {
+                        k_nms_resolve_next<<<1, NMS_THREADS, smem, st>>>(sbox.as<float4>(), sarea.as<float>(), supp.as<uint8_t>(),
+                                                                         keepf.as<uint8_t>(), s0, m, iou_thr, kbox, karea, bs);
+                        Y3_LAUNCHED(ctx);
+                        k_nms_apply_from<<<blocks, 256, 0, st>>>(sbox.as<float4>(), sarea.as<float>(), supp.as<uint8_t>(), s0, m,
+                                                                 iou_thr, kbox, karea, bs);
+                        Y3_LAUNCHED(ctx);
+                    }
+                    step += burst;
+                    Y3_CUDA(cudaMemcpyAsync(h_bs, bs, sizeof(BigState), cudaMemcpyDeviceToHost, st));
+                    Y3_CUDA(cudaStreamSynchronize(st));
+                    if (h_bs->done) break;
+                }
+                continue;
+            }
             for (int64_t c0 = 0; c0 < m; c0 += NMS_T) {
                 const int ct = (int)std::min<int64_t>(NMS_T, m - c0);
                 k_nms_resolve<<<1, NMS_THREADS, smem, st>>>(sbox.as<float4>(), sarea.as<float>(), supp.as<uint8_t>(),
