@@ -480,23 +480,64 @@ k_nms_small(const float4* __restrict__ sbox, const float* __restrict__ sarea, ui
     }
 }
 
+// Gathers (in order) the indices of the next <= NMS_T still-alive boxes of a segment behind *s_pos into s_idx and
+// advances *s_pos past the last position examined.  All NMS_THREADS threads call it; returns the count.
+__device__ __forceinline__ int gather_alive(const uint8_t* __restrict__ supp, int64_t s0, long long m, long long* s_pos, int* s_n,
+                                            int* s_idx, int* s_wcount) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) *s_n = 0;
+    __syncthreads();
+    while (true) {
+        const long long pos = *s_pos;
+        const int have = *s_n;
+        if (pos >= m || have >= NMS_T) break;
+        const long long p = pos + threadIdx.x;
+        const bool alive = p < m && supp[s0 + p] == 0;
+        const unsigned b = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) s_wcount[wid] = __popc(b);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < NMS_THREADS / 32; ++w) { const int c = s_wcount[w]; if (w < wid) before += c; total += c; }
+        const int rank = have + before + __popc(b & ((1u << lane) - 1u));
+        if (alive && rank < NMS_T) s_idx[rank] = (int)p;
+        // positions consumed: the whole window if everything fitted, else up to the alive box that took the last slot
+        __syncthreads();
+        if (have + total <= NMS_T) {
+            if (threadIdx.x == 0) { *s_n = have + total; *s_pos = min(pos + (long long)NMS_THREADS, m); }
+        } else {
+            if (alive && rank == NMS_T - 1) { *s_n = NMS_T; *s_pos = p + 1; }
+        }
+        __syncthreads();
+    }
+    return *s_n;
+}
+
 __global__ void __launch_bounds__(NMS_THREADS)
 k_nms_segments(const float4* __restrict__ sbox, const float* __restrict__ sarea, uint8_t* __restrict__ supp,
                uint8_t* __restrict__ keepf, const int64_t* __restrict__ seg_off, int nseg, float thr,
                int64_t big_segment, int64_t small_segment) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ChunkSmem& S = *reinterpret_cast<ChunkSmem*>(smem_raw);
+    __shared__ int s_idx[NMS_T];
+    __shared__ int s_wcount[NMS_THREADS / 32];
+    __shared__ int s_n;
+    __shared__ long long s_pos;
     for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
         const int64_t s0 = seg_off[seg];
         const int64_t m = seg_off[seg + 1] - s0;
         if (m <= small_segment || m > big_segment) continue;       // small ones: k_nms_small
-        for (int64_t c0 = 0; c0 < m; c0 += NMS_T) {
-            const int ct = (int)min((int64_t)NMS_T, m - c0);
-            chunk_resolve(S, sbox, sarea, supp, s0 + c0, ct, thr);
+        // steps of <= NMS_T still-alive boxes (gathered behind a cursor, so boxes that earlier steps suppressed
+        // cost nothing any more): resolve the step, then apply its kept boxes to the rest of the segment
+        if (threadIdx.x == 0) s_pos = 0;
+        __syncthreads();
+        while (true) {
+            const int ct = gather_alive(supp, s0, (long long)m, &s_pos, &s_n, s_idx, s_wcount);
+            if (ct == 0) break;
+            chunk_resolve(S, sbox, sarea, supp, s0, ct, thr, s_idx);
             const int nk = S.nk;
-            for (int t = threadIdx.x; t < nk; t += NMS_THREADS) keepf[s0 + c0 + S.klist[t]] = 1;
-            // apply this chunk's kept boxes to the rest of the segment
-            for (int64_t j = c0 + ct + threadIdx.x; j < m; j += NMS_THREADS) {
+            for (int t = threadIdx.x; t < nk; t += NMS_THREADS) keepf[s0 + s_idx[S.klist[t]]] = 1;
+            const long long first = s_pos;
+            for (long long j = first + threadIdx.x; j < m; j += NMS_THREADS) {
                 if (supp[s0 + j]) continue;
                 const float4 bj = sbox[s0 + j];
                 const float aj = sarea[s0 + j];
@@ -568,36 +609,13 @@ k_nms_resolve_next(const float4* __restrict__ sbox, const float* __restrict__ sa
     __shared__ int s_wcount[NMS_THREADS / 32];
     __shared__ int s_n;
     __shared__ long long s_pos;
-    if (threadIdx.x == 0) { s_n = 0; s_pos = st->cursor; }
+    if (threadIdx.x == 0) s_pos = st->cursor;
     __syncthreads();
     if (s_pos >= m) {
         if (threadIdx.x == 0) { st->knum = 0; st->done = 1; }
         return;
     }
-    // gather: windows of NMS_THREADS positions, ordered compaction of the alive ones into s_idx
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    while (true) {
-        const long long pos = s_pos;
-        const int have = s_n;
-        if (pos >= m || have >= NMS_T) break;
-        const long long p = pos + threadIdx.x;
-        const bool alive = p < m && supp[s0 + p] == 0;
-        const unsigned b = __ballot_sync(0xffffffffu, alive);
-        if (lane == 0) s_wcount[wid] = __popc(b);
-        __syncthreads();
-        int before = 0, total = 0;
-        for (int w = 0; w < NMS_THREADS / 32; ++w) { const int c = s_wcount[w]; if (w < wid) before += c; total += c; }
-        const int rank = have + before + __popc(b & ((1u << lane) - 1u));
-        if (alive && rank < NMS_T) s_idx[rank] = (int)p;
-        // positions consumed: the whole window if everything fitted, else up to the alive box that took the last slot
-        __syncthreads();
-        if (have + total <= NMS_T) {
-            if (threadIdx.x == 0) { s_n = have + total; s_pos = min(pos + (long long)NMS_THREADS, (long long)m); }
-        } else {
-            if (alive && rank == NMS_T - 1) { s_n = NMS_T; s_pos = p + 1; }
-        }
-        __syncthreads();
-    }
+    gather_alive(supp, s0, (long long)m, &s_pos, &s_n, s_idx, s_wcount);
     const int ct = s_n;
     if (ct > 0) chunk_resolve(S, sbox, sarea, supp, s0, ct, thr, s_idx);
     const int nk = ct > 0 ? S.nk : 0;
