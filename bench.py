@@ -281,7 +281,7 @@ def main():
                           "peak_source": peak_src,
                           # dram__bytes_read+write of ONE launch from ncu --set full (profiles/r1_ncu_conv_tc2_256_*.txt:
                           # conv2d_11, 3x3 128->256 @64x64 + residual, 64 tiles; algorithmic bytes of that launch 335.5 MB)
-                          "traffic": 2.988e8, "traffic_launch": "k_conv_tc2<256,2> conv2d_11 @64 tiles",
+                          "traffic": 3.010e8, "traffic_launch": "k_conv_tc2h<256> conv2d_11 @64 tiles (profiles/r1_ncu_conv_tc2h_256_*.txt)",
                           "traffic_algorithmic_bytes": 3.355e8,
                           "flops_per_step_this_rank": count * CONV_GF_PER_TILE * 1e9, "conv_ms_per_step": conv_ms},
                 stages_ms=stages, stages_ms_e2e=stages_e2e, lib_ms_total_e2e=tlast_e2e["ms_total"], boxes=n_boxes, candidates_per_step=int(tlast["candidates"]),
