@@ -635,9 +635,15 @@ y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dt, y3_mem img_m
         BandUpload U = begin_band_upload(h, T, img, dt, img_mem, W, C, geo, tile_first, tile_count);
         const void* d_img = U.dev;
         const long long row_lo = U.row_lo;
+        // tiles of the batch that starts at t0.  With the image in host memory the first batch is short, so that the
+        // convolutions start after a small upload and the rest of the band streams in behind them.
+        auto batch_tiles = [&](int64_t t0) {
+            const int64_t full = (U.host && t0 == 0) ? std::min<int64_t>(net->maxB, 48) : net->maxB;
+            return (int)std::min<int64_t>(full, tile_count - t0);
+        };
         auto rows_needed = [&](int64_t t0) {                  // last image row (exclusive) batch t0 reads
             int need = 0;
-            const int64_t n = std::min<int64_t>(net->maxB, tile_count - t0);
+            const int64_t n = batch_tiles(t0);
             for (int64_t t = 0; t < n; ++t) need = std::max(need, geo[tile_first + t0 + t].y1);
             return need;
         };
@@ -675,15 +681,15 @@ y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dt, y3_mem img_m
         };
         int64_t prev_t0 = -1; int prev_nb = 0, prev_set = 0; cudaEvent_t prev_ev = nullptr;
         int it = 0;
-        for (int64_t t0 = 0; t0 < tile_count; t0 += B, ++it) {
-            const int nb = (int)std::min<int64_t>(B, tile_count - t0);
+        for (int64_t t0 = 0; t0 < tile_count; t0 += batch_tiles(t0), ++it) {
+            const int nb = batch_tiles(t0);
             const TileGeo* g = d_geo + tile_first + t0;
             const int set = it & 1;
             {   // wait for this batch's rows, then start the next batch's upload so it overlaps this batch's compute
                 Phase p(h, &Tm.ms_h2d);
                 if (ready) Y3_CUDA(cudaStreamWaitEvent(h->stream, ready, 0));
                 p.stop();
-                if (t0 + B < tile_count) ready = upload_rows_until(h, U, rows_needed(t0 + B));
+                if (t0 + nb < tile_count) ready = upload_rows_until(h, U, rows_needed(t0 + nb));
             }
             { Phase p(h, &Tm.ms_prep); launch_tile_norm(h, d_img, dt, row_lo, (int)W, C, g, nb, th, tw, T->tiles.as<float>(), nullptr, T->sums.as<double>()); p.stop(); }
             { Phase p(h, &Tm.ms_conv); net->forward(T->tiles.as<float>(), nb, set); p.stop(); }
