@@ -25,42 +25,49 @@ def inference(image_folder, image_format, saved_model_filepath, output_folder, m
     for i, fp in enumerate(files):
         file_name = os.path.basename(fp)
         print('{}/{} : {}'.format(i, len(files), file_name))
-        img = imagereader.imread(fp)
-        height, width, channels = img.shape
-        img = imagereader.zscore_normalize(img.astype(np.float32))
-        print('  img.shape={}'.format(img.shape))
-        batch = np.ascontiguousarray(img.transpose((2, 0, 1))[None], dtype=np.float32)
-        boxes = np.array(yolo_model(batch, training=False))[0]
-        boxes[:, 0] = np.clip(boxes[:, 0], 0, width)
-        boxes[:, 1] = np.clip(boxes[:, 1], 0, height)
-        boxes[:, 2] = np.clip(boxes[:, 2], 0, width)
-        boxes[:, 3] = np.clip(boxes[:, 3], 0, height)
-        boxes = bbox_utils.filter_small_boxes(boxes, min_box_size)
-        kept, scores, labels = bbox_utils.per_class_nms(boxes[:, 0:4], boxes[:, 4:5], boxes[:, 5:])
-        if kept is None:
-            out = np.zeros((0, 5), np.int32)
-        else:
-            kept = kept.copy()
-            kept[:, 2] -= kept[:, 0]
-            kept[:, 3] -= kept[:, 1]
-            out = np.concatenate((kept, labels.reshape(-1, 1)), axis=-1).astype(np.int32)
-        print('Found: {} rois'.format(out.shape[0]))
-        bbox_utils.write_boxes_from_xywhc(out, os.path.join(output_folder, file_name.replace(image_format, 'csv')))
+        rois = _detect_one(yolo_model, imagereader.imread(fp), min_box_size)
+        print('Found: {} rois'.format(rois.shape[0]))
+        bbox_utils.write_boxes_from_xywhc(rois, os.path.join(output_folder, file_name.replace(image_format, 'csv')))
+
+
+def _detect_one(yolo_model, img, min_box_size):
+    """One image through the model: z-score, forward + decode, clip to the image, small-box filter, per-class NMS
+    -> int32 [n, 5] rows x, y, w, h, class (inference.py:47-98)."""
+    if img.ndim == 2:
+        img = img[:, :, None]
+    height, width = img.shape[0], img.shape[1]
+    norm = imagereader.zscore_normalize(img.astype(np.float32))
+    print('  img.shape={}'.format(norm.shape))
+    batch = np.ascontiguousarray(norm.transpose((2, 0, 1))[None], dtype=np.float32)
+    dets = np.array(yolo_model(batch, training=False))[0]
+    for col, hi in ((0, width), (1, height), (2, width), (3, height)):
+        dets[:, col] = np.clip(dets[:, col], 0, hi)
+    dets = bbox_utils.filter_small_boxes(dets, min_box_size)
+    kept, _, labels = bbox_utils.per_class_nms(dets[:, 0:4], dets[:, 4:5], dets[:, 5:])
+    if kept is None:
+        return np.zeros((0, 5), np.int32)
+    xywh = kept.copy()
+    xywh[:, 2] -= xywh[:, 0]
+    xywh[:, 3] -= xywh[:, 1]
+    return np.concatenate((xywh, labels.reshape(-1, 1)), axis=-1).astype(np.int32)
+
+
+def _parse_args(argv=None):
+    """Same flags and defaults as the reference CLI (inference.py:103-114)."""
+    ap = argparse.ArgumentParser(prog="inference", description="YOLOv3 detection over a folder of images (B200 path)")
+    ap.add_argument("--saved-model-filepath", type=str, required=True, help="model directory (TF SavedModel or y3 side-car)")
+    ap.add_argument("--output-folder", type=str, required=True, help="where the per-image CSV files go")
+    ap.add_argument("--image-folder", dest="image_folder", type=str, required=True, help="folder with the input images")
+    ap.add_argument("--image-format", dest="image_format", type=str, default="tif", help="image file extension, e.g. tif, jpg, png")
+    ap.add_argument("--min-box-size", type=int, default=32, help="drop detections not larger than this in both directions")
+    return ap.parse_args(argv)
 
 
 if __name__ == "__main__":
-    parser = argparse.ArgumentParser(prog='inference', description='Script to detect stars with the selected model')
-    parser.add_argument('--saved-model-filepath', type=str, required=True, help='Filepath to the saved model to use')
-    parser.add_argument('--output-folder', type=str, required=True)
-    parser.add_argument('--image-folder', dest='image_folder', type=str, required=True,
-                        help='filepath to the folder containing tif images to inference (Required)')
-    parser.add_argument('--image-format', dest='image_format', type=str, default='tif',
-                        help='format (extension) of the input images. E.g {tif, jpg, png)')
-    parser.add_argument('--min-box-size', type=int, default=32, help='Smallest detection to consider. Default (32, 32).')
-    args = parser.parse_args()
-    print('Arguments:')
-    for k, v in sorted(vars(args).items()):
-        print('{} = {}'.format(k, v))
-    os.environ["CUDA_DEVICE_ORDER"] = "PCI_BUS_ID"
-    os.environ["CUDA_VISIBLE_DEVICES"] = "0"       # the reference pins inference.py to GPU 0 (inference.py:131-133)
-    inference(args.image_folder, args.image_format, args.saved_model_filepath, args.output_folder, args.min_box_size)
+    cli = _parse_args()
+    print("Arguments:")
+    for key in sorted(vars(cli)):
+        print("{} = {}".format(key, getattr(cli, key)))
+    # the reference pins inference.py to GPU 0 (inference.py:131-133)
+    os.environ.update(CUDA_DEVICE_ORDER="PCI_BUS_ID", CUDA_VISIBLE_DEVICES="0")
+    inference(cli.image_folder, cli.image_format, cli.saved_model_filepath, cli.output_folder, cli.min_box_size)
