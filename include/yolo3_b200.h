@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define Y3_ABI_VERSION 1
+#define Y3_ABI_VERSION 2   /* 2: + y3_zscore */
 #define Y3_MAX_ANCHORS 8
 
 typedef int32_t y3_status;

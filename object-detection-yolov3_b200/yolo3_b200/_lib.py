@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libyolo3_b200.so")
 Y3_MAX_ANCHORS = 8
 MEM_HOST, MEM_DEVICE = 0, 1
 U8, U16, I32, F32 = 0, 1, 2, 3
+ABI_VERSION = 2            # include/yolo3_b200.h Y3_ABI_VERSION this binding was written against
 OK, ERR_INVALID, ERR_CUDA, ERR_NOSPACE, ERR_STATE, ERR_UNSUPPORTED, ERR_NODEVICE = 0, -1, -2, -3, -4, -5, -6
 
 
@@ -84,6 +85,9 @@ def load():
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    if lib.y3_abi_version() < ABI_VERSION:
+        raise RuntimeError("%s has ABI version %d, this package needs >= %d - rebuild it (`python __graft_entry__.py`)"
+                           % (LIB_PATH, lib.y3_abi_version(), ABI_VERSION))
     _lib = lib
     return lib
 
