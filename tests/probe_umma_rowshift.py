@@ -1,5 +1,5 @@
 """Hardware probe (GPU): which UMMA descriptor convention reads row-shifted SWIZZLE_128B tiles correctly."""
-import ctypes, os, sys
+import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "object-detection-yolov3_b200"))

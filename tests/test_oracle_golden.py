@@ -1,8 +1,6 @@
 """The oracle (NumPy + C restatements) against the committed golden vectors that
 oracle/gen_golden.py minted from the reference's own code.  CPU only."""
-import contextlib
 import hashlib
-import io
 
 import numpy as np
 import pytest
