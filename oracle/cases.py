@@ -114,3 +114,13 @@ PIPE_CASES = dict(e96=(1200, 1500, 1, np.uint16, (512, 512), 96, 900, 2, 32),
                   e64=(1000, 1300, 1, np.uint16, (512, 512), 64, 700, 1, 32),
                   rgb=(700, 640, 3, np.uint8, (256, 256), 32, 400, 3, 24),
                   one=(300, 280, 1, np.uint16, (512, 512), 96, 300, 1, 32))
+
+
+def merge_case(n, canvas, seed, wh=(10, 60)):
+    """integer-coordinate boxes + distinct scores for bbox_utils.union_all_overlapping_bb (exact in fp32 and fp64)"""
+    rng = np.random.default_rng(seed)
+    c = rng.integers(0, canvas, (n, 2))
+    half = rng.integers(wh[0] // 2, wh[1] // 2, (n, 2))
+    boxes = np.concatenate([c - half, c + half], axis=1).astype(np.int64)
+    scores = (rng.permutation(n).astype(np.float64) + 1.0) / (n + 1.0)
+    return boxes, scores

@@ -112,6 +112,17 @@ def main():
     it.EDGE_EFFECT_RANGE = 96
     np.savez_compressed(os.path.join(OUT, "tiled_pipeline.npz"), **g)
 
+    # ---- union_all_overlapping_bb (off the hot path; bbox_utils.py:138-197) ------------------
+    g = {}
+    for tag, (n, canvas, seed, thr) in dict(sparse=(60, 600, 1, 0), dense=(120, 300, 2, 0), thr=(150, 400, 3, 0.2),
+                                            single=(1, 50, 4, 0)).items():
+        b, s = cases.merge_case(n, canvas, seed)
+        mb, ms = bu.union_all_overlapping_bb(b.copy(), s.copy(), thr)
+        g[tag + "_boxes"] = np.asarray(mb, np.float64)
+        g[tag + "_scores"] = np.asarray(ms, np.float64)
+        print("merge", tag, n, "->", len(ms))
+    np.savez_compressed(os.path.join(OUT, "box_merge.npz"), **g)
+
     # ---- K3: 200k boxes (reference verbatim, ~75 s) ----------------------------------------
     p = os.path.join(OUT, "nms_k3.npz")
     if args.full or not os.path.exists(p):

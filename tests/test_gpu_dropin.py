@@ -154,3 +154,22 @@ def test_tf_saved_model_directory_is_a_drop_in(tmp_path):
         inference_tiled.CROSS_SEAM_NMS = False
     rows4 = (tmp_path / "o4" / "a.csv").read_text().splitlines()
     assert set(rows4) <= set(a.splitlines()) and len(rows4) >= 2
+
+
+def test_bbox_utils_off_path_helpers(tmp_path, golden):
+    """the non-hot-path helpers of the bbox_utils facade: box merge (IoU on the GPU) against the reference's output,
+    CSV writers / loaders round trip"""
+    import bbox_utils
+    g = golden("box_merge.npz")
+    for tag, (n, canvas, seed, thr) in dict(sparse=(60, 600, 1, 0), dense=(120, 300, 2, 0), thr=(150, 400, 3, 0.2),
+                                            single=(1, 50, 4, 0)).items():
+        b, s = cases.merge_case(n, canvas, seed)
+        mb, ms = bbox_utils.union_all_overlapping_bb(b.copy(), s.copy(), thr)
+        assert np.array_equal(np.asarray(mb, np.float64), g[tag + "_boxes"]), tag
+        assert np.allclose(np.asarray(ms, np.float64), g[tag + "_scores"], rtol=0, atol=1e-12), tag
+    rows = np.array([[5, 7, 20, 31, 1], [0, 0, 3, 3, 0]], np.int64)
+    p = str(tmp_path / "b.csv")
+    bbox_utils.write_boxes_from_ltrbc(rows, p)
+    assert np.array_equal(bbox_utils.load_boxes_to_ltrbc(p), rows.astype(np.float64))
+    assert bbox_utils.load_boxes_to_xywhc(p).tolist() == [[5, 7, 16, 25, 1], [0, 0, 4, 4, 0]]
+    assert bbox_utils.load_boxes_to_ltrbc(str(tmp_path / "missing.csv")).shape == (0, 5)
