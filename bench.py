@@ -276,7 +276,7 @@ def main():
                 e2e={"value": mpix / (ms_e2e * 1e-3), "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
                      "d2h_bytes_per_step": n_boxes * 48, "ms_per_step": ms_e2e},
                 gpu_launches=int(launches),
-                roofline={"bound": "tensor", "kernel": "k_conv_tc (all conv launches of the step, rank 0)",
+                roofline={"bound": "tensor", "kernel": "conv stack of the step on rank 0: k_conv_tc2h<256> (57 % of kernel time) + k_conv_tc2 / k_conv_halo / k_stem_conv1 / k_conv_tc",
                           "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tf / peak_tf,
                           "peak_source": peak_src,
                           # dram__bytes_read+write of ONE launch from ncu --set full (profiles/r1_ncu_conv_tc2_256_*.txt:
