@@ -55,7 +55,17 @@ class YoloV3:
     def get_keras_feature_map_model(self):
         return self.model_feature_maps
 
-    def save(self, path):
+    def save(self, path, fmt="y3"):
+        """fmt="y3": y3_config.json + y3_weights.npz; fmt="tf": the reference's SavedModel layout (variables/ bundle +
+        a saved_model.pb that carries the input signature) plus y3_config.json for the anchors."""
+        if fmt == "tf":
+            import json
+            import os
+            from yolo3_b200 import tf_bundle
+            tf_bundle.write_saved_model_variables(path, self.weights, input_shape=[-1, self.img_size[2], self.img_size[0], self.img_size[1]])
+            with open(os.path.join(path, _weights.CONFIG_FILE), "w") as fh:
+                json.dump({"anchors": [[float(a), float(b)] for a, b in self.anchors]}, fh)
+            return
         _weights.save_model_dir(path, self.weights, self.img_size, self.number_classes, self.anchors)
 
     def get_optimizer(self):
