@@ -770,7 +770,7 @@ y3_status y3_debug_layer_output(y3_handle h, const char* layer, int32_t batch, f
     const int64_t n = (int64_t)batch * op->out.c * t.h * t.w;
     Y3_CHECK(n <= cap_floats, Y3_ERR_NOSPACE, "need %lld floats", (long long)n);
     h->stage_out.reserve((size_t)n * 4);
-    slice_to_nchw(h, reinterpret_cast<const __nv_bfloat16*>(t.ptr), h->stage_out.as<float>(), batch, t.h, t.w, op->out.c, t.c, op->out.coff);
+    slice_to_nchw(h, reinterpret_cast<const __nv_bfloat16*>(t.ptr), h->stage_out.as<float>(), batch, t.h, t.w, op->out.c, t.c, op->out.coff, t.f16);
     from_device(h, out, Y3_MEM_HOST, h->stage_out.p, (size_t)n * 4);
     Y3_CUDA(cudaStreamSynchronize(h->stream));
     Y3_API_END(h)

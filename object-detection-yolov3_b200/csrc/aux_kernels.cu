@@ -9,6 +9,7 @@
 //   k_heads_to_nchw   [B,HW,pitch] fp32 -> NCHW fp32 (the parity point of y3_forward_heads)
 //   k_decode          reorg_layer + convert_feature_map_to_inference_detections (model.py:122-212)
 #include "aux_kernels.cuh"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace y3 {
@@ -111,8 +112,15 @@ void launch_stem(y3_context* ctx, const float* in, __nv_bfloat16* out, const flo
 }
 
 // ------------------------------------------------------------------------------------------ packing
+// 16-bit operand element: bf16, or fp16 for layers of the fp16 tail (values beyond the half range saturate)
+__device__ __forceinline__ __nv_bfloat16 to_operand16(float v, bool f16) {
+    if (!f16) return __float2bfloat16_rn(v);
+    const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    return *reinterpret_cast<const __nv_bfloat16*>(&h);
+}
+
 __global__ void k_pack_conv_w(const float* __restrict__ k /*[taps,Cin,Cout]*/, __nv_bfloat16* __restrict__ out,
-                              int taps, int cin, int cout, int cout_pad) {
+                              int taps, int cin, int cout, int cout_pad, int f16) {
     const long long n = (long long)cout_pad * taps * cin;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int ci = (int)(i % cin);
@@ -120,12 +128,12 @@ __global__ void k_pack_conv_w(const float* __restrict__ k /*[taps,Cin,Cout]*/, _
         const int tap = (int)(r % taps);
         const int co = (int)(r / taps);
         const float v = co < cout ? k[((long long)tap * cin + ci) * cout + co] : 0.f;
-        out[i] = __float2bfloat16_rn(v);
+        out[i] = to_operand16(v, f16 != 0);
     }
 }
-__global__ void k_pack_convt_w(const float* __restrict__ k /*[4,Cout,Cin]*/, __nv_bfloat16* __restrict__ out, long long n) {
+__global__ void k_pack_convt_w(const float* __restrict__ k /*[4,Cout,Cin]*/, __nv_bfloat16* __restrict__ out, long long n, int f16) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        out[i] = __float2bfloat16_rn(k[i]);
+        out[i] = to_operand16(k[i], f16 != 0);
 }
 __global__ void k_bn_fold(const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ m,
                           const float* __restrict__ v, float* __restrict__ s, float* __restrict__ t, int c) {
@@ -141,7 +149,8 @@ __global__ void k_bn_fold(const float* __restrict__ g, const float* __restrict__
 // route columns copied, bias' = by + sum_co Wy[co,k] * bt[co].   Wy: Keras [2C, cout]; Kt: Keras [2,2,C_up,C_x].
 __global__ void k_compose_up(const float* __restrict__ wy, const float* __restrict__ kt, const float* __restrict__ by,
                              const float* __restrict__ bt, int c_up, int c_x, int c_r, int cout,
-                             __nv_bfloat16* __restrict__ w_out /*[4][cout][c_x+c_r]*/, float* __restrict__ b_out) {
+                             __nv_bfloat16* __restrict__ w_out /*[4][cout][c_x+c_r]*/, float* __restrict__ b_out,
+                             int x_f16, int r_f16) {
     const int K = c_x + c_r;
     const long long n = 4LL * cout * K;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -157,7 +166,7 @@ __global__ void k_compose_up(const float* __restrict__ wy, const float* __restri
         } else {
             acc = wy[(long long)(c_up + kk - c_x) * cout + k];
         }
-        w_out[i] = __float2bfloat16_rn(acc);
+        w_out[i] = to_operand16(acc, (kk < c_x ? x_f16 : r_f16) != 0);     // each K segment in its tensor's format
         if (ij == 0 && kk == 0) {
             float b = by[k];
             for (int co = 0; co < c_up; ++co) b = fmaf(wy[(long long)co * cout + k], bt[co], b);
@@ -166,19 +175,20 @@ __global__ void k_compose_up(const float* __restrict__ wy, const float* __restri
     }
 }
 void compose_up(y3_context* ctx, const float* wy, const float* kt, const float* by, const float* bt, int c_up, int c_x, int c_r,
-                int cout, __nv_bfloat16* w_out, float* b_out) {
+                int cout, __nv_bfloat16* w_out, float* b_out, bool x_f16, bool r_f16) {
     const long long n = 4LL * cout * (c_x + c_r);
-    k_compose_up<<<(int)std::min<long long>((n + 255) / 256, 8192), 256, 0, ctx->stream>>>(wy, kt, by, bt, c_up, c_x, c_r, cout, w_out, b_out);
+    k_compose_up<<<(int)std::min<long long>((n + 255) / 256, 8192), 256, 0, ctx->stream>>>(wy, kt, by, bt, c_up, c_x, c_r, cout, w_out, b_out,
+                                                                                           x_f16 ? 1 : 0, r_f16 ? 1 : 0);
     Y3_LAUNCHED(ctx);
 }
 
-void pack_conv_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, int taps, int cin, int cout, int cout_pad) {
+void pack_conv_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, int taps, int cin, int cout, int cout_pad, bool f16) {
     const long long n = (long long)cout_pad * taps * cin;
-    k_pack_conv_w<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, ctx->stream>>>(k, out, taps, cin, cout, cout_pad);
+    k_pack_conv_w<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, ctx->stream>>>(k, out, taps, cin, cout, cout_pad, f16 ? 1 : 0);
     Y3_LAUNCHED(ctx);
 }
-void pack_convt_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, long long n) {
-    k_pack_convt_w<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, ctx->stream>>>(k, out, n);
+void pack_convt_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, long long n, bool f16) {
+    k_pack_convt_w<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, ctx->stream>>>(k, out, n, f16 ? 1 : 0);
     Y3_LAUNCHED(ctx);
 }
 void bn_fold(y3_context* ctx, const float* g, const float* b, const float* m, const float* v, float* s, float* t, int c) {
@@ -204,7 +214,7 @@ void heads_to_nchw(y3_context* ctx, const float* in, float* out, int B, int HW, 
 }
 
 __global__ void k_slice_to_nchw(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
-                                int pitch, int coff) {
+                                int pitch, int coff, int f16) {
     const long long n = (long long)B * C * H * W;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int x = (int)(i % W);
@@ -212,12 +222,13 @@ __global__ void k_slice_to_nchw(const __nv_bfloat16* __restrict__ in, float* __r
         const int y = (int)(r % H); r /= H;
         const int c = (int)(r % C);
         const int b = (int)(r / C);
-        out[i] = __bfloat162float(in[(((long long)b * H + y) * W + x) * pitch + coff + c]);
+        const __nv_bfloat16 e = in[(((long long)b * H + y) * W + x) * pitch + coff + c];
+        out[i] = f16 ? __half2float(*reinterpret_cast<const __half*>(&e)) : __bfloat162float(e);
     }
 }
-void slice_to_nchw(y3_context* ctx, const __nv_bfloat16* in, float* out, int B, int H, int W, int C, int pitch, int coff) {
+void slice_to_nchw(y3_context* ctx, const __nv_bfloat16* in, float* out, int B, int H, int W, int C, int pitch, int coff, bool f16) {
     const long long n = (long long)B * C * H * W;
-    k_slice_to_nchw<<<(int)std::min<long long>((n + 255) / 256, 8192), 256, 0, ctx->stream>>>(in, out, B, H, W, C, pitch, coff);
+    k_slice_to_nchw<<<(int)std::min<long long>((n + 255) / 256, 8192), 256, 0, ctx->stream>>>(in, out, B, H, W, C, pitch, coff, f16 ? 1 : 0);
     Y3_LAUNCHED(ctx);
 }
 

@@ -51,13 +51,14 @@ void launch_stem(y3_context* ctx, const float* in, __nv_bfloat16* out, const flo
 // tensor-core stem (stem_tc.cu); returns false when the channel count is not covered
 bool launch_stem_tc(y3_context* ctx, const float* in, __nv_bfloat16* out, const float* w, const float* bias, const float* scale,
                     const float* shift, int B, int H, int W, int cin);
-void pack_conv_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, int taps, int cin, int cout, int cout_pad);
-void pack_convt_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, long long n);
+// f16: pack as fp16 instead of bf16 (layers whose input tensor is fp16 - the tail after the first upsample)
+void pack_conv_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, int taps, int cin, int cout, int cout_pad, bool f16 = false);
+void pack_convt_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, long long n, bool f16 = false);
 void compose_up(y3_context* ctx, const float* wy, const float* kt, const float* by, const float* bt, int c_up, int c_x, int c_r,
-                int cout, __nv_bfloat16* w_out, float* b_out);
+                int cout, __nv_bfloat16* w_out, float* b_out, bool x_f16 = false, bool r_f16 = false);
 void bn_fold(y3_context* ctx, const float* g, const float* b, const float* m, const float* v, float* s, float* t, int c);
 void heads_to_nchw(y3_context* ctx, const float* in, float* out, int B, int HW, int C, int pitch);
-void slice_to_nchw(y3_context* ctx, const __nv_bfloat16* in, float* out, int B, int H, int W, int C, int pitch, int coff);
+void slice_to_nchw(y3_context* ctx, const __nv_bfloat16* in, float* out, int B, int H, int W, int C, int pitch, int coff, bool f16 = false);
 void launch_decode(y3_context* ctx, const DecodeArgs& D, float* out);
 
 }  // namespace y3

@@ -173,7 +173,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (one thread)
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN);
+            const uint32_t idesc1 = P.in_f16 ? make_idesc_f16(TILE_M, BN) : make_idesc_bf16(TILE_M, BN);
+            const uint32_t idesc2 = P.in2_f16 ? make_idesc_f16(TILE_M, BN) : make_idesc_bf16(TILE_M, BN);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -183,7 +184,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 mbar_wait(&tmem_empty[p], (use & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(p * BN);
+                int kc = 0;
                 for (int ki = 0; ki < k_iters; ++ki) {
+                    const uint32_t idesc = kc < P.k_split ? idesc1 : idesc2;
+                    if (++kc == P.kchunks) kc = 0;
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(stage_base + stage * C::STAGE_BYTES);
@@ -272,8 +276,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                             yy[4] += bf16lo(x.z); yy[5] += bf16hi(x.z); yy[6] += bf16lo(x.w); yy[7] += bf16hi(x.w);
                         }
                         uint4 o;
-                        o.x = pack_bf16x2(yy[0], yy[1]); o.y = pack_bf16x2(yy[2], yy[3]);
-                        o.z = pack_bf16x2(yy[4], yy[5]); o.w = pack_bf16x2(yy[6], yy[7]);
+                        o.x = pack_act2(yy[0], yy[1], P.out_f16); o.y = pack_act2(yy[2], yy[3], P.out_f16);
+                        o.z = pack_act2(yy[4], yy[5], P.out_f16); o.w = pack_act2(yy[6], yy[7], P.out_f16);
                         *dst = o;
                     }
                 }

@@ -21,6 +21,8 @@ struct ConvArgs {
     int im_ho, im_wo;        //   output grid of one image
     int im_stride, im_lower; //   traversal stride and lower pixel-box corner (= -pad_before)
     int has_res, linear, out_f32;
+    int in_f16, in2_f16;     // operand format of the K chunks read through map_a / map_a2 (and of their weights): fp16 instead of bf16
+    int out_f16;             // the output activation tensor is fp16 (the fp16 tail after the first upsample, net.cu)
     int Ho, Wo;
     const float* bias;       // [cout_pad]
     const float* scale;      // [cout_pad]  gamma / sqrt(var + eps)       (unused when linear)

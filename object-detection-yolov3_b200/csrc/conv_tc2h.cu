@@ -164,7 +164,8 @@ k_conv_tc2h(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (leader CTA, one thread)
         if (rank == 0 && lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(256, BN2);
+            const uint32_t idesc1 = P.in_f16 ? make_idesc_f16(256, BN2) : make_idesc_bf16(256, BN2);
+            const uint32_t idesc2 = P.in2_f16 ? make_idesc_f16(256, BN2) : make_idesc_bf16(256, BN2);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -174,7 +175,10 @@ k_conv_tc2h(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 mbar_wait(&tmem_empty[p], (use & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(p * BN2);
+                int kc = 0;
                 for (int ki = 0; ki < k_iters; ++ki) {
+                    const uint32_t idesc = kc < P.k_split ? idesc1 : idesc2;
+                    if (++kc == P.kchunks) kc = 0;
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(stage_base + stage * C::STAGE_BYTES);
@@ -308,8 +312,8 @@ k_conv_tc2h(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                                 yy[6] += __uint_as_float(x.w << 16); yy[7] += __uint_as_float(x.w & 0xffff0000u);
                             }
                             uint4 o;
-                            o.x = pack2h(yy[0], yy[1]); o.y = pack2h(yy[2], yy[3]);
-                            o.z = pack2h(yy[4], yy[5]); o.w = pack2h(yy[6], yy[7]);
+                            o.x = pack_act2(yy[0], yy[1], P.out_f16); o.y = pack_act2(yy[2], yy[3], P.out_f16);
+                            o.z = pack_act2(yy[4], yy[5], P.out_f16); o.w = pack_act2(yy[6], yy[7], P.out_f16);
                             *dst = o;
                         }
                     }

@@ -10,6 +10,7 @@ static constexpr int HEAD_PITCH_MAX = 256;   // fp32 channels per pixel of a sto
 
 struct TensorInfo {
     int h = 0, w = 0, c = 0;
+    bool f16 = false;         // stored as fp16 instead of bf16 (tensors of the tail after the first upsample)
     int first = -1, last = -1;
     void* ptr = nullptr;
     size_t bytes = 0;
@@ -66,6 +67,7 @@ struct Net {
     std::string missing = "all layers";
     int cur_batch = -1;
     int n_conv = 0, n_bn = 0, n_convt = 0;
+    bool tail_f16 = false;          // tensors created from now on are fp16 (set after the first detection layer)
 
     explicit Net(y3_context* c) : ctx(c) {}
     ~Net();

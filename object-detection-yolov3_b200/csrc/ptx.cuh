@@ -7,6 +7,8 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace y3 { namespace ptx {
@@ -188,6 +190,22 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
 // bf16 x bf16 -> fp32, both operands K-major, M x N tile
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// fp16 x fp16 -> fp32 (a_format = b_format = 0): same tensor-core rate, 11-bit significand (the fp16 tail, net.cu)
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
+    return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// two floats -> packed 16-bit pair for an activation tensor: bf16 (round to nearest even) or fp16 with the
+// magnitude clamped to the largest finite half (an overflow saturates instead of turning into inf)
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi, int f16) {
+    if (f16) {
+        lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+        hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+        const __half2 v = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<const uint32_t*>(&v);
+    }
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
 }
 
 }}  // namespace y3::ptx

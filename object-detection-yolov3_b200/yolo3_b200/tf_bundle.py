@@ -486,6 +486,169 @@ def signature_input_shape(saved_model_pb):
         return None
 
 
+_AUTO_NAME = None
+
+
+def normalize_keras_names(found):
+    """Keras auto-names count layers per PROCESS, not per model: the reference trainer builds a second YoloV3 in the
+    same process before tf.saved_model.save (train.py:213-221), so its export holds conv2d_72 .. conv2d_143,
+    batch_normalization_72 .., conv2d_transpose_2/_3 instead of conv2d .. conv2d_71.  Renumber every auto-named
+    family relative to the smallest suffix present, so that names count from zero ("conv2d", "conv2d_1", ...).
+    Explicitly named layers (feature_map_1..3) are left alone.  {name: array} -> {name: array}."""
+    import re
+    global _AUTO_NAME
+    if _AUTO_NAME is None:
+        _AUTO_NAME = re.compile(r"^(conv2d_transpose|conv2d|batch_normalization)(?:_(\d+))?$")
+    lowest = {}
+    for name in found:
+        layer = name.split("/")[0]
+        m = _AUTO_NAME.match(layer)
+        if m:
+            k = int(m.group(2)) if m.group(2) else 0
+            lowest[m.group(1)] = min(lowest.get(m.group(1), k), k)
+    out = {}
+    for name, arr in found.items():
+        layer, _, var = name.partition("/")
+        m = _AUTO_NAME.match(layer)
+        if m:
+            k = (int(m.group(2)) if m.group(2) else 0) - lowest[m.group(1)]
+            layer = m.group(1) if k == 0 else "%s_%d" % (m.group(1), k)
+        key = layer + "/" + var
+        if key in out:
+            raise BundleError("two variables map to %s after renumbering the Keras auto-names" % key)
+        out[key] = arr
+    return out
+
+
+def _tensor_proto(buf):
+    """TensorProto{dtype=1, tensor_shape=2, tensor_content=4, float_val=5, double_val=6, int_val=7, int64_val=10}
+    -> ndarray or None (only the numeric kinds an anchor table can have)."""
+    dtype, shape, content, vals = 0, (), None, []
+    for fn, wt, v in proto_fields(buf):
+        if fn == 1:
+            dtype = v
+        elif fn == 2:
+            shape = _parse_shape(v)
+        elif fn == 4:
+            content = bytes(v)
+        elif fn in (5, 6, 7, 10):
+            if wt == 2:                                   # packed
+                if fn == 5:
+                    vals += list(struct.unpack("<%df" % (len(v) // 4), v))
+                elif fn == 6:
+                    vals += list(struct.unpack("<%dd" % (len(v) // 8), v))
+                else:
+                    pos = 0
+                    while pos < len(v):
+                        x, pos = _varint(v, pos)
+                        vals.append(_signed64(x))
+            elif wt == 5:
+                vals.append(struct.unpack("<f", v)[0])
+            elif wt == 1:
+                vals.append(struct.unpack("<d", v)[0])
+            else:
+                vals.append(_signed64(v))
+    np_dt = {1: np.float32, 2: np.float64, 3: np.int32, 9: np.int64}.get(dtype)
+    if np_dt is None:
+        return None
+    count = int(np.prod(shape, dtype=np.int64)) if shape else 1
+    if content is not None and len(content) == count * np.dtype(np_dt).itemsize:
+        return np.frombuffer(content, dtype=np_dt).reshape(shape).astype(np.float64)
+    if len(vals) == count:
+        return np.asarray(vals, np.float64).reshape(shape)
+    if len(vals) == 1:                                    # a splat constant
+        return np.full(shape, vals[0], np.float64)
+    return None
+
+
+def _node_defs(buf):
+    """[(name, op, [inputs], {attr: AttrValue bytes})] of the NodeDef messages in `buf` fields `field`."""
+    name = op = None
+    inputs, attrs = [], {}
+    for fn, _, v in proto_fields(buf):
+        if fn == 1:
+            name = v.decode("utf-8", "replace")
+        elif fn == 2:
+            op = v.decode("utf-8", "replace")
+        elif fn == 3:
+            inputs.append(v.decode("utf-8", "replace"))
+        elif fn == 5:
+            k = val = None
+            for f2, _, v2 in proto_fields(v):
+                if f2 == 1:
+                    k = v2.decode("utf-8", "replace")
+                elif f2 == 2:
+                    val = v2
+            if k is not None:
+                attrs[k] = val
+    return name, op, inputs, attrs
+
+
+def _anchor_tables(nodes):
+    """anchor tables among the nodes of ONE graph / function body: the [A,2] constant operand of a Mul
+    (model.py:163 `box_wh = tf.exp(box_wh) * self.anchors`), looked up through Cast / Identity."""
+    by_name = {n[0]: n for n in nodes}
+
+    def const_of(ref, depth=0):
+        node = by_name.get(ref.lstrip("^").split(":")[0])
+        if node is None or depth > 4:
+            return None
+        if node[1] == "Const" and node[3].get("value") is not None:
+            for fn, _, v in proto_fields(node[3]["value"]):
+                if fn == 8:
+                    return _tensor_proto(v)
+            return None
+        if node[1] in ("Cast", "Identity") and node[2]:
+            return const_of(node[2][0], depth + 1)
+        return None
+
+    out = []
+    for _, op, inputs, _ in nodes:
+        if op != "Mul" or len([i for i in inputs if not i.startswith("^")]) != 2:
+            continue
+        for ref in inputs:
+            t = const_of(ref)
+            if t is not None and t.ndim == 2 and t.shape[1] == 2 and 1 <= t.shape[0] <= 8 and np.all(np.isfinite(t)) and np.all(t > 0):
+                out.append([(float(w), float(h)) for w, h in t])
+    return out
+
+
+def saved_model_anchors(saved_model_pb):
+    """The anchor table [(w, h), ...] baked into the graph of a reference SavedModel, or None.
+    The anchors are not variables: `YoloV3.reorg_layer` multiplies exp(t_wh) by the Python list `self.anchors`
+    (model.py:163, 432-436), which TensorFlow embeds as a Const of shape [A, 2] feeding a Mul - once per scale, in the
+    top-level graph or in a function of the library.  SavedModel{meta_graphs=2}; MetaGraphDef{graph_def=2};
+    GraphDef{node=1, library=2}; FunctionDefLibrary{function=1}; FunctionDef{node_def=3}; NodeDef{name=1, op=2,
+    input=3, attr=5}; AttrValue{tensor=8}.  All tables found must agree; disagreement or none -> None.
+    PARITY UNPINNED (no TensorFlow-written file available): validated on hand-assembled protos only."""
+    try:
+        with open(saved_model_pb, "rb") as fh:
+            buf = fh.read()
+        tables = []
+        for fn, wt, mg in proto_fields(buf):
+            if fn != 2 or wt != 2:
+                continue
+            for f2, w2, gd in proto_fields(mg):
+                if f2 != 2 or w2 != 2:
+                    continue
+                top = []
+                for f3, w3, v in proto_fields(gd):
+                    if f3 == 1 and w3 == 2:
+                        top.append(_node_defs(v))
+                    elif f3 == 2 and w3 == 2:
+                        for f4, w4, fdef in proto_fields(v):
+                            if f4 != 1 or w4 != 2:
+                                continue
+                            body = [_node_defs(nd) for f5, w5, nd in proto_fields(fdef) if f5 == 3 and w5 == 2]
+                            tables += _anchor_tables(body)
+                tables += _anchor_tables(top)
+        if not tables or any(t != tables[0] for t in tables):
+            return None
+        return tables[0]
+    except (OSError, BundleError, IndexError, struct.error, UnicodeDecodeError):
+        return None
+
+
 # ------------------------------------------------------------------------------------------ writer (tests, export)
 def write_bundle(prefix, tensors, strings=None, checksum_limit=None):
     """tensors: {key: ndarray}; strings: {key: bytes} scalar string tensors.  One data shard.
@@ -518,10 +681,29 @@ def write_bundle(prefix, tensors, strings=None, checksum_limit=None):
     write_table(prefix + ".index", items)
 
 
-def write_saved_model_variables(path, weights, input_shape=None, checksum_limit=None):
+def _anchor_function(anchors):
+    """FunctionDef with the decode's `exp(t_wh) * anchors` nodes (what saved_model_anchors looks for)."""
+    a = np.asarray(anchors, np.float32).reshape(-1, 2)
+    shape = b"".join(_pb_bytes(2, _pb_int(1, int(d))) for d in a.shape)
+    tensor = _pb_int(1, 1) + _pb_bytes(2, shape) + _pb_bytes(4, a.tobytes())
+
+    def attr(key, val):
+        return _pb_bytes(5, _pb_bytes(1, key) + _pb_bytes(2, val))
+
+    def node(name, op, inputs, attrs=b""):
+        return _pb_bytes(3, _pb_bytes(1, name) + _pb_bytes(2, op) + b"".join(_pb_bytes(3, i) for i in inputs) + attrs)
+
+    body = node(b"Exp", b"Exp", [b"inputs"], attr(b"T", _pb_int(6, 1)))
+    body += node(b"mul/y", b"Const", [], attr(b"dtype", _pb_int(6, 1)) + attr(b"value", _pb_bytes(8, tensor)))
+    body += node(b"mul", b"Mul", [b"Exp:y:0", b"mul/y:output:0"], attr(b"T", _pb_int(6, 1)))
+    return _pb_bytes(1, _pb_bytes(1, b"__inference_reorg_layer")) + body
+
+
+def write_saved_model_variables(path, weights, input_shape=None, checksum_limit=None, anchors=None):
     """Writes `<path>/variables/variables.{index,data-*}` the way tf.saved_model.save lays a Keras model out
     (layer_with_weights-<i>/<attr>/.ATTRIBUTES/VARIABLE_VALUE keys + object graph) and, when input_shape
-    ([-1, C, H, W]) is given, a minimal saved_model.pb that carries only the serving signature's input shape."""
+    ([-1, C, H, W]) is given, a minimal saved_model.pb that carries the serving signature's input shape and - when
+    anchors are given - the decode's anchor constant as a library function (`exp(t_wh) * anchors`)."""
     layers = []
     for name in weights:
         layer = name.split("/")[0]
@@ -547,5 +729,7 @@ def write_saved_model_variables(path, weights, input_shape=None, checksum_limit=
         tinfo = _pb_bytes(1, b"serving_default_input_1:0") + _pb_int(2, 1) + _pb_bytes(3, shape)
         sig = _pb_bytes(1, _pb_bytes(1, b"input_1") + _pb_bytes(2, tinfo)) + _pb_bytes(3, b"tensorflow/serving/predict")
         mg = _pb_bytes(5, _pb_bytes(1, b"serving_default") + _pb_bytes(2, sig))
+        if anchors is not None:                               # graph_def{library{function{...}}}
+            mg = _pb_bytes(2, _pb_bytes(2, _pb_bytes(1, _anchor_function(anchors)))) + mg
         with open(os.path.join(path, "saved_model.pb"), "wb") as fh:
             fh.write(_pb_int(1, 1) + _pb_bytes(2, mg))

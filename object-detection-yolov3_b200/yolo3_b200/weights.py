@@ -6,7 +6,8 @@ The reference keeps weights in a TF SavedModel (train.py:221, inference.py:35). 
 available here, so a model directory is either
   * the reference's own SavedModel: `saved_model.pb` + `variables/variables.{index,data-*}` - the variable bundle
     is parsed without TensorFlow by tf_bundle.py (anchors are graph constants that the bundle does not hold: they
-    come from an optional y3_config.json next to saved_model.pb, else the reference defaults of model.py:433), or
+    come from y3_config.json next to saved_model.pb, else from the constants in saved_model.pb, else from the
+    Y3_ANCHORS environment variable - never from a silent default), or
   * the TensorFlow-free side-car format written by save_model_dir():
     <dir>/y3_config.json     {"img_size":[H,W,C], "number_classes":NC, "anchors":[[w,h],...]}
     <dir>/y3_weights.npz     one fp32 array per Keras variable name, Keras layouts
@@ -115,7 +116,7 @@ def save_model_dir(path, weights, img_size, number_classes, anchors):
     np.savez(os.path.join(path, WEIGHTS_FILE), **{k: np.asarray(v, np.float32) for k, v in weights.items()})
 
 
-def load_model_dir(path):
+def load_model_dir(path, anchors=None):
     """-> (config dict, {name: fp32 array}).  cfg["img_size"] may hold None for H/W when the directory is a
     TF SavedModel whose signature does not pin them (the engine is then built for the size it is called with)."""
     cfg_p, w_p = os.path.join(path, CONFIG_FILE), os.path.join(path, WEIGHTS_FILE)
@@ -129,25 +130,58 @@ def load_model_dir(path):
         return cfg, weights
     prefix = os.path.join(path, "variables", "variables")
     if os.path.exists(prefix + ".index"):
-        return _load_tf_saved_model(path, prefix, cfg)
+        return _load_tf_saved_model(path, prefix, cfg, anchors)
     raise RuntimeError("%s holds neither %s + %s nor a TensorFlow SavedModel (variables/variables.index)"
                        % (path, CONFIG_FILE, WEIGHTS_FILE))
 
 
-def _load_tf_saved_model(path, prefix, cfg):
+def _anchors_from_env():
+    """Y3_ANCHORS="64,384;384,64" - for SavedModels whose graph constants cannot be read."""
+    txt = os.environ.get("Y3_ANCHORS")
+    if not txt:
+        return None
+    try:
+        out = [tuple(float(v) for v in pair.split(",")) for pair in txt.replace(" ", "").split(";") if pair]
+    except ValueError:
+        out = None
+    if not out or any(len(a) != 2 for a in out):
+        raise RuntimeError("Y3_ANCHORS must look like '64,384;384,64', got %r" % txt)
+    return out
+
+
+def _load_tf_saved_model(path, prefix, cfg, anchors=None):
+    """anchors: explicit [(w,h), ...] (wins over everything else).  Otherwise, in this order: y3_config.json next to
+    saved_model.pb, the anchor constants of the graph in saved_model.pb (model.py:163, 432-436), the Y3_ANCHORS
+    environment variable.  There is NO silent default: anchors are not variables, a wrong table gives wrong boxes
+    (and a wrong class count - train.py:33 uses 2 anchors) without any error."""
     from . import tf_bundle
-    from .engine import DEFAULT_ANCHORS
-    found = tf_bundle.read_keras_variables(prefix)
+    found = tf_bundle.normalize_keras_names(tf_bundle.read_keras_variables(prefix))
     stem = found.get("conv2d/kernel")
     head = found.get("feature_map_1/kernel")
     if stem is None or head is None or stem.ndim != 4 or head.ndim != 4:
         raise RuntimeError("%s: the variable bundle does not hold the YOLOv3 layers (conv2d/kernel, feature_map_1/kernel)" % path)
     c_img, det_c = int(stem.shape[2]), int(head.shape[3])
-    anchors = [tuple(a) for a in cfg["anchors"]] if cfg and "anchors" in cfg else list(DEFAULT_ANCHORS)
+    pb = os.path.join(path, "saved_model.pb")
+    source = "argument"
+    if anchors is None and cfg and "anchors" in cfg:
+        anchors, source = [tuple(a) for a in cfg["anchors"]], CONFIG_FILE
+    if anchors is None:
+        anchors, source = tf_bundle.saved_model_anchors(pb), "saved_model.pb"
+    if anchors is None:
+        anchors, source = _anchors_from_env(), "Y3_ANCHORS"
+    if anchors is None:
+        raise RuntimeError("%s: the anchors of this model are unknown - they are graph constants, not variables, and could not "
+                           "be read from saved_model.pb.  Write them into %s ({\"anchors\": [[w,h],...]}) next to "
+                           "saved_model.pb or set Y3_ANCHORS='w,h;w,h' (the reference trainer uses 64,384;384,64 - "
+                           "train.py:33; model.py:433 defaults to 32,32;128,128;256,256)" % (path, CONFIG_FILE))
+    anchors = [(float(a), float(b)) for a, b in anchors]
     if det_c % len(anchors) or det_c // len(anchors) < 6:
-        raise RuntimeError("%s: %d detection channels do not fit %d anchors; put the training anchors into %s"
-                           % (path, det_c, len(anchors), CONFIG_FILE))
+        raise RuntimeError("%s: %d detection channels do not fit the %d anchors from %s"
+                           % (path, det_c, len(anchors), source))
     nc = det_c // len(anchors) - 5
+    if cfg and "number_classes" in cfg and int(cfg["number_classes"]) != nc:
+        raise RuntimeError("%s: %s says %d classes but %d detection channels / %d anchors give %d"
+                           % (path, CONFIG_FILE, int(cfg["number_classes"]), det_c, len(anchors), nc))
     weights = {}
     for name, shape in variable_inventory(c_img, nc, len(anchors)):
         if name not in found:
@@ -159,7 +193,8 @@ def _load_tf_saved_model(path, prefix, cfg):
     if cfg and "img_size" in cfg:
         hw = [int(cfg["img_size"][0]), int(cfg["img_size"][1])]
     else:
-        sig = tf_bundle.signature_input_shape(os.path.join(path, "saved_model.pb"))       # [-1, C, H, W]
+        sig = tf_bundle.signature_input_shape(pb)       # [-1, C, H, W]
         if sig and sig[2] > 0 and sig[3] > 0:
             hw = [int(sig[2]), int(sig[3])]
-    return {"img_size": [hw[0], hw[1], c_img], "number_classes": nc, "anchors": [[float(a), float(b)] for a, b in anchors]}, weights
+    return {"img_size": [hw[0], hw[1], c_img], "number_classes": nc, "anchors": [[a, b] for a, b in anchors],
+            "anchors_source": source}, weights

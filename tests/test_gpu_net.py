@@ -48,15 +48,11 @@ def test_layers_small_net():
         assert mt.heads_rel_err(a, b.numpy()) <= HEAD_TOL
 
 
-TAIL_NOTE = ("bf16 storage of the fm3 tail: the all-ones upsample makes the last ~7 layers 8x more sensitive to "
-             "rounding than the backbone.  Measured on B200 over 3 weight draws (tests/head_error_sweep.py): this "
-             "2-anchor / 1-class family gives fm3 = 0.7 %, 2.0 %, 2.2 %; the 3-anchor configs give 0.96-1.24 %.  "
-             "Matches the CPU bf16 emulation of the oracle (DESIGN.md 'numerics') - inherent to bf16, not a kernel fault.")
+REF_ANCHORS = [(64, 384), (384, 64)]      # the reference trainer's own anchors (train.py:33)
 
 
 @pytest.mark.parametrize("cfg", [((416, 416, 3), 80, None, 1), ((512, 512, 1), 1, None, 2),
-                                 pytest.param(((512, 512, 1), 1, [(64, 384), (384, 64)], 1),
-                                              marks=pytest.mark.xfail(reason=TAIL_NOTE, strict=False)),
+                                 ((512, 512, 1), 1, REF_ANCHORS, 1),
                                  ((608, 608, 3), 80, None, 1),
                                  # 1-channel, not a multiple of 256 wide, odd batch: partial row segments and an idle image slot
                                  # in the fused stem + conv2d_1 kernel and the halo kernels
@@ -70,6 +66,43 @@ def test_heads_vs_oracle(cfg):
     errs = [mt.heads_rel_err(a, b.numpy()) for a, b in zip(got, want)]
     print(cfg, errs)
     assert all(a.shape == tuple(b.shape) for a, b in zip(got, want))
+    assert max(errs) <= HEAD_TOL, errs
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5])
+def test_heads_reference_training_config_over_weight_draws(seed):
+    """The reference's own configuration (512x512x1, 1 class, anchors (64,384),(384,64): train.py:33, model.py:108-120)
+    over several weight draws.  With bf16 storage of the tail after the first upsample this config sat AT the 2e-2 bar
+    (fm3 0.7 / 2.0 / 2.2 % over three draws, fm2 up to 1.8 %); the fp16 tail (net.cu) holds it with a wide margin,
+    so the bound asserted here is 1e-2 - a regression of the tail numerics fails the test."""
+    eng, ora = make((512, 512, 1), 1, REF_ANCHORS, max_batch=1, seed=seed)
+    x = torch.randn(1, 1, 512, 512, generator=torch.Generator().manual_seed(2))
+    want = ora.feature_maps(x)
+    got = eng.forward_heads(x.numpy())
+    errs = [mt.heads_rel_err(a, b.numpy()) for a, b in zip(got, want)]
+    print("seed", seed, errs)
+    assert max(errs) <= 1e-2, errs
+
+
+def test_heads_with_random_transposed_conv_weights():
+    """upsample_2x is a general Conv2DTranspose(k2,s2) (model.py:94-105): its kernel starts as all ones but is a
+    trainable variable.  Random kernel and bias: the composed up-conv path must follow the oracle's conv_transpose."""
+    from yolo3_b200 import Engine
+    img_size, nc = (256, 320, 3), 3
+    W = mt.init_weights(3, nc, 3, seed=7, randomize_bn=True)
+    g = torch.Generator().manual_seed(11)
+    for name in ("conv2d_transpose", "conv2d_transpose_1"):
+        k = W[name + "/kernel"]
+        W[name + "/kernel"] = (torch.rand(k.shape, generator=g) * 2 - 1) * (3.0 / k.shape[3]) ** 0.5
+        W[name + "/bias"] = torch.randn(k.shape[2], generator=g) * 0.1
+    eng = Engine(img_size, nc, None, max_batch=2)
+    eng.load_weights({k: v.numpy() for k, v in W.items()})
+    ora = mt.OracleNet(W, img_size, nc)
+    x = torch.randn(2, 3, 256, 320, generator=torch.Generator().manual_seed(5))
+    want = ora.feature_maps(x)
+    got = eng.forward_heads(x.numpy())
+    errs = [mt.heads_rel_err(a, b.numpy()) for a, b in zip(got, want)]
+    print(errs)
     assert max(errs) <= HEAD_TOL, errs
 
 

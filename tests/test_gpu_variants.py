@@ -13,7 +13,7 @@ HEAD_TOL = 2e-2
 
 VARIANTS = [{}, {"Y3_NO_HALO": "1"}, {"Y3_NO_WS2": "1"}, {"Y3_NO_STEM_FUSE": "1"}, {"Y3_NO_STEM_FUSE": "1", "Y3_STEM_FP32": "1"},
             {"Y3_DISABLE_2CTA": "1"}, {"Y3_CONV2_OLD": "1"}, {"Y3_NO_IM2COL": "1", "Y3_NO_HALO": "1"}, {"Y3_NO_UPFUSE": "1"},
-            {"Y3_PDL": "1"}]
+            {"Y3_PDL": "1"}, {"Y3_TAIL_BF16": "1"}]
 
 
 @pytest.mark.parametrize("env", VARIANTS, ids=lambda e: "+".join(sorted(e)) or "default")
