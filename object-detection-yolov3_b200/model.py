@@ -62,7 +62,8 @@ class YoloV3:
             import json
             import os
             from yolo3_b200 import tf_bundle
-            tf_bundle.write_saved_model_variables(path, self.weights, input_shape=[-1, self.img_size[2], self.img_size[0], self.img_size[1]])
+            tf_bundle.write_saved_model_variables(path, self.weights, input_shape=[-1, self.img_size[2], self.img_size[0], self.img_size[1]],
+                                                  anchors=self.anchors)
             with open(os.path.join(path, _weights.CONFIG_FILE), "w") as fh:
                 json.dump({"anchors": [[float(a), float(b)] for a, b in self.anchors]}, fh)
             return
@@ -81,8 +82,8 @@ class LoadedModel:
     y3_config.json + y3_weights.npz side-car format.  The network is fully convolutional: when the model
     directory does not pin the input size the engine is built for the first size it is asked for."""
 
-    def __init__(self, saved_model_filepath, max_batch=1, device=0):
-        cfg, w = _weights.load_model_dir(saved_model_filepath)
+    def __init__(self, saved_model_filepath, max_batch=1, device=0, anchors=None):
+        cfg, w = _weights.load_model_dir(saved_model_filepath, anchors=anchors)
         self._weights, self._max_batch, self._device = w, max_batch, device
         self._c_img = int(cfg["img_size"][2])
         self.number_classes = int(cfg["number_classes"])
@@ -111,5 +112,7 @@ class LoadedModel:
         return self.engine_for(batch.shape[2:4]).forward_boxes(batch)
 
 
-def load_saved_model(saved_model_filepath, max_batch=1, device=0):
-    return LoadedModel(saved_model_filepath, max_batch=max_batch, device=device)
+def load_saved_model(saved_model_filepath, max_batch=1, device=0, anchors=None):
+    """anchors: only needed for a TF SavedModel whose anchor constants cannot be read from saved_model.pb and that has no
+    y3_config.json (see yolo3_b200/weights.py); there is no silent default."""
+    return LoadedModel(saved_model_filepath, max_batch=max_batch, device=device, anchors=anchors)

@@ -31,6 +31,23 @@ def _ptr(a):
     raise TypeError(type(a))
 
 
+def _image_arg(img):
+    """(array, y3_dtype) for an HWC image the tiling entry points accept.  The library reads u8 / u16 / i32 / f32;
+    anything else is converted the way the reference does for every tile (`astype(np.float32)`, inference_tiled.py:202),
+    or exactly to int32 where that is lossless (int8 / int16 / bool)."""
+    if isinstance(img, np.ndarray):
+        if img.dtype not in _DTYPES:
+            img = img.astype(np.int32 if img.dtype in (np.dtype(np.int8), np.dtype(np.int16), np.dtype(np.bool_)) else np.float32)
+        return np.ascontiguousarray(img), _DTYPES[img.dtype]
+    import torch
+    table = {torch.uint8: _lib.U8, torch.int32: _lib.I32, torch.float32: _lib.F32}
+    if getattr(torch, "uint16", None) is not None:
+        table[torch.uint16] = _lib.U16
+    if img.dtype not in table:
+        img = img.to(torch.int32 if img.dtype in (torch.int8, torch.int16, torch.bool) else torch.float32)
+    return img.contiguous(), table[img.dtype]
+
+
 def _capsule(t):
     if isinstance(t, np.ndarray):
         return np.ascontiguousarray(t, dtype=np.float32).__dlpack__()
@@ -142,7 +159,7 @@ class Engine:
         img: HWC numpy (host) or torch CUDA tensor.  Returns float64 [n,6] (numpy, or a torch CUDA
         tensor when out_device is a torch device - used for the NCCL all-gather)."""
         H, W, C = (int(v) for v in img.shape)
-        dt = _DTYPES[np.dtype(img.dtype)] if isinstance(img, np.ndarray) else _torch_dtype(img)
+        img, dt = _image_arg(img)
         p, mem = _ptr(img)
         cap = int(cap) if cap else getattr(self, "_tiled_cap", 1 << 16)
         while True:
@@ -168,8 +185,9 @@ class Engine:
         total = tile_count(H, W, tile_size, edge_range)
         count = total - first if count is None else count
         out = np.empty((count, C, int(tile_size[0]), int(tile_size[1])), np.float32)
+        img, dt = _image_arg(img)
         p, mem = _ptr(img)
-        check(self.lib.y3_tiles_normalized(self.h, p, _DTYPES[np.dtype(img.dtype)], mem, H, W, C, int(tile_size[0]),
+        check(self.lib.y3_tiles_normalized(self.h, p, dt, mem, H, W, C, int(tile_size[0]),
                                            int(tile_size[1]), int(edge_range), first, count, out.ctypes.data, MEM_HOST), self.h)
         return out
 
@@ -187,11 +205,13 @@ class Engine:
         H, W, C = (int(v) for v in img.shape)
         total = tile_count(H, W, tile_size, edge_range)
         count = total - first if count is None else count
+        src_dtype = img.dtype
+        img, dt = _image_arg(img)
         out = np.empty((count, int(tile_size[0]), int(tile_size[1]), C), img.dtype)
         p, mem = _ptr(img)
-        check(self.lib.y3_tiles_raw(self.h, p, _DTYPES[np.dtype(img.dtype)], mem, H, W, C, int(tile_size[0]),
+        check(self.lib.y3_tiles_raw(self.h, p, dt, mem, H, W, C, int(tile_size[0]),
                                     int(tile_size[1]), int(edge_range), first, count, out.ctypes.data, MEM_HOST), self.h)
-        return out
+        return out if out.dtype == src_dtype else out.astype(src_dtype)      # tiles come back in the source dtype
 
     def stitch_tiles(self, dets, img_hw, tile_size, min_box_size=32, edge_range=96, iou_threshold=0.3,
                      score_threshold=0.1, first=0):
@@ -311,12 +331,6 @@ class Engine:
         ms = ctypes.c_float()
         check(self.lib.y3_bench_forward(self.h, int(batch), int(iters), ctypes.byref(ms)), self.h)
         return ms.value
-
-
-def _torch_dtype(t):
-    import torch
-    return {torch.uint8: _lib.U8, torch.int32: _lib.I32, torch.float32: _lib.F32,
-            getattr(torch, "uint16", None): _lib.U16, torch.int16: _lib.U16}[t.dtype]
 
 
 def seam_candidates(pred, img_hw, tile_size, edge_range):

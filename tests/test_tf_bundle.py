@@ -82,7 +82,9 @@ def test_saved_model_directory_round_trip(tmp_path):
     tb.write_saved_model_variables(d, w, input_shape=[-1, 1, 384, 512], checksum_limit=1 << 16)
     assert os.path.exists(os.path.join(d, "saved_model.pb")) and os.path.exists(os.path.join(d, "variables", "variables.index"))
     assert tb.signature_input_shape(os.path.join(d, "saved_model.pb")) == [-1, 1, 384, 512]
-    cfg, got = weights.load_model_dir(d)
+    with pytest.raises(RuntimeError, match="anchors of this model are unknown"):      # no silent default
+        weights.load_model_dir(d)
+    cfg, got = weights.load_model_dir(d, anchors=[(32, 32), (128, 128), (256, 256)])
     assert cfg["img_size"] == [384, 512, 1] and cfg["number_classes"] == 2 and len(cfg["anchors"]) == 3
     assert sorted(got) == sorted(w)
     for k in w:
@@ -97,3 +99,58 @@ def test_saved_model_directory_round_trip(tmp_path):
     json.dump({"anchors": [[12, 12], [24, 24], [48, 48]], "img_size": [256, 256, 1]}, open(os.path.join(d, "y3_config.json"), "w"))
     cfg3, _ = weights.load_model_dir(d)
     assert cfg3["anchors"] == [[12.0, 12.0], [24.0, 24.0], [48.0, 48.0]] and cfg3["img_size"] == [256, 256, 1]
+
+
+def _small_weights(nc, na, seed):
+    return weights.random_init(1, nc, na, seed=seed, randomize_bn=True)
+
+
+def test_reference_trainer_style_saved_model(tmp_path, monkeypatch):
+    """A directory laid out the way the reference trainer's export is (train.py:213-221), written by an independent
+    encoder (tests/tf_fixture.py: google.protobuf messages, LevelDB table with really-snappy-compressed blocks, two data
+    shards): Keras names shifted by the first model built in the process (conv2d_72 ..), `layer_with_weights-N` not in
+    creation order, anchors only as graph constants.  2 anchors x (5 + 4 classes) = 18 channels - the case that used to
+    load silently as 3 anchors x 1 class."""
+    import tf_fixture
+    anchors = [(64, 384), (384, 64)]
+    w = _small_weights(4, 2, seed=9)
+    d = str(tmp_path / "saved_model")
+    tf_fixture.write_reference_style_saved_model(d, w, anchors, [-1, 1, 512, 512])
+    raw_names = set(tb.read_keras_variables(os.path.join(d, "variables", "variables")))
+    assert "conv2d_72/kernel" in raw_names and "conv2d/kernel" not in raw_names and "conv2d_transpose_3/kernel" in raw_names
+    assert tb.saved_model_anchors(os.path.join(d, "saved_model.pb")) == [(64.0, 384.0), (384.0, 64.0)]
+    cfg, got = weights.load_model_dir(d)
+    assert cfg["anchors"] == [[64.0, 384.0], [384.0, 64.0]] and cfg["number_classes"] == 4 and cfg["anchors_source"] == "saved_model.pb"
+    assert cfg["img_size"] == [512, 512, 1]
+    assert sorted(got) == sorted(w)
+    for k in w:
+        assert np.array_equal(got[k], w[k]), k
+    # the table really is snappy-compressed with copy tags, and every tensor checksum that was written verifies
+    tab = open(os.path.join(d, "variables", "variables.index"), "rb").read()
+    assert tab[-8:] == (0xdb4775248b80fb57).to_bytes(8, "little")
+    small = {k for k, v in tb.read_bundle(os.path.join(d, "variables", "variables")).items() if isinstance(v, np.ndarray) and v.nbytes <= 1 << 16}
+    assert len(small) > 300
+    tb.read_bundle(os.path.join(d, "variables", "variables"), keys=small, verify=True)
+
+    # graph constants unreadable -> loud failure, unless the anchors are supplied some other way
+    d2 = str(tmp_path / "saved_model_no_consts")
+    tf_fixture.write_reference_style_saved_model(d2, w, anchors, [-1, 1, 512, 512], with_anchor_consts=False)
+    monkeypatch.delenv("Y3_ANCHORS", raising=False)
+    with pytest.raises(RuntimeError, match="anchors of this model are unknown"):
+        weights.load_model_dir(d2)
+    monkeypatch.setenv("Y3_ANCHORS", "64,384;384,64")
+    cfg2, _ = weights.load_model_dir(d2)
+    assert cfg2["number_classes"] == 4 and cfg2["anchors_source"] == "Y3_ANCHORS"
+    monkeypatch.setenv("Y3_ANCHORS", "32,32;128,128;256,256;64,64;8,8")        # 18 channels / 5 anchors: refused
+    with pytest.raises(RuntimeError, match="do not fit"):
+        weights.load_model_dir(d2)
+
+
+def test_keras_name_renumbering():
+    found = {"conv2d_72/kernel": 1, "conv2d_73/kernel": 2, "conv2d_143/bias": 3, "batch_normalization_72/gamma": 4,
+             "batch_normalization_80/beta": 5, "conv2d_transpose_2/kernel": 6, "conv2d_transpose_3/bias": 7, "feature_map_2/kernel": 8}
+    out = tb.normalize_keras_names(found)
+    assert out == {"conv2d/kernel": 1, "conv2d_1/kernel": 2, "conv2d_71/bias": 3, "batch_normalization/gamma": 4,
+                   "batch_normalization_8/beta": 5, "conv2d_transpose/kernel": 6, "conv2d_transpose_1/bias": 7, "feature_map_2/kernel": 8}
+    same = {"conv2d/kernel": 1, "conv2d_1/kernel": 2, "conv2d_transpose/kernel": 3}
+    assert tb.normalize_keras_names(same) == same
