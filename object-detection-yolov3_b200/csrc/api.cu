@@ -37,40 +37,6 @@ static thread_local std::string g_create_error;
 
 namespace {
 
-cudaEvent_t take_event(y3_context* c) {
-    if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
-    cudaEvent_t e;
-    Y3_CUDA(cudaEventCreate(&e));
-    return e;
-}
-// Times a stage with two events on the stream; nothing blocks until flush_phases().
-struct Phase {
-    y3_context* c;
-    cudaEvent_t a;
-    float* dst;
-    bool open = true;
-    Phase(y3_context* ctx, float* d) : c(ctx), a(take_event(ctx)), dst(d) { cudaEventRecord(a, c->stream); }
-    void stop() {
-        if (!open) return;
-        open = false;
-        cudaEvent_t b = take_event(c);
-        cudaEventRecord(b, c->stream);
-        c->phase_log.push_back({a, b, dst});
-    }
-    ~Phase() { if (open) c->event_pool.push_back(a); }
-};
-void flush_phases(y3_context* c) {
-    cudaStreamSynchronize(c->stream);
-    for (auto& r : c->phase_log) {
-        float t = 0.f;
-        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) *r.dst += t;
-        c->event_pool.push_back(r.a);
-        c->event_pool.push_back(r.b);
-    }
-    c->phase_log.clear();
-    cudaGetLastError();
-}
-
 const void* to_device(y3_context* c, const void* p, y3_mem mem, size_t bytes, DevBuf& stage) {
     if (mem == Y3_MEM_DEVICE) return p;
     stage.reserve(bytes);
@@ -282,9 +248,9 @@ y3_status y3_detect(y3_handle h, const float* in, y3_mem in_mem, int32_t batch, 
     NmsResult R;
     {   // decode + score + threshold + small-box filter + compaction fused in one pass over the heads
         Phase p(h, &T.ms_nms);
-        R = post_of(h)->run(heads_source(net, batch, true, min_box, score_thr), iou_thr);
-        p.stop();
-        T.ms_decode = post_of(h)->last_cand_ms;      // the fused decode+threshold+compaction kernel alone
+        post_of(h)->enqueue(heads_source(net, batch, true, min_box, score_thr), iou_thr);
+        p.stop();                                    // (ms_decode: the fused decode+threshold+compaction kernel alone)
+        R = post_of(h)->finish();
     }
     T.candidates = R.n_cand; T.kept = R.n_kept;
     *n_out = R.n_kept;
@@ -368,7 +334,7 @@ y3_status y3_single_class_nms(y3_handle h, const float* boxes, const float* scor
         s.box = d_box; s.box_stride = 4; s.cls = d_sc; s.cls_stride = 1; s.obj = nullptr;
         s.rows_per_image = m; s.n_images = 1; s.nc = 1; s.raw_scores = true;
         NmsResult R;
-        { Phase p(h, &T.ms_nms); R = post_of(h)->run(s, iou_thr); p.stop(); }
+        { Phase p(h, &T.ms_nms); post_of(h)->enqueue(s, iou_thr); p.stop(); R = post_of(h)->finish(); }
         *n_keep = R.n_kept;
         T.candidates = R.n_cand; T.kept = R.n_kept;
         { Phase p(h, &T.ms_d2h);
@@ -404,7 +370,7 @@ y3_status y3_per_class_nms(y3_handle h, const float* boxes, const float* obj, co
         s.box = d_box; s.box_stride = 4; s.obj = d_obj; s.obj_stride = 1; s.cls = d_cls; s.cls_stride = nc;
         s.rows_per_image = n; s.n_images = 1; s.nc = nc; s.score_thr = score_thr;
         NmsResult R;
-        { Phase p(h, &T.ms_nms); R = post_of(h)->run(s, iou_thr); p.stop(); }
+        { Phase p(h, &T.ms_nms); post_of(h)->enqueue(s, iou_thr); p.stop(); R = post_of(h)->finish(); }
         *n_out = R.n_kept;
         T.candidates = R.n_cand; T.kept = R.n_kept;
         Y3_CHECK(R.n_kept <= cap, Y3_ERR_NOSPACE, "output capacity %lld < %lld kept boxes", (long long)cap, (long long)R.n_kept);
@@ -506,7 +472,39 @@ const TileGeo* upload_geo(y3_context* h, Tiler* T, const std::vector<TileGeo>& g
     Y3_CUDA(cudaStreamSynchronize(h->stream));     // geo is a host temporary
     return T->geo.as<TileGeo>();
 }
-void deliver_preds(y3_context* h, Tiler* T, double* preds, y3_mem mem, int64_t cap, int64_t* n_out) {
+// Output of the tiled path.  Segmented pipeline: the rows are written by the NMS emit kernel straight into the caller's
+// buffer when that lives on the device, else into T->acc (capacity = the caller's), and the row count stays on the
+// device until finish_stitch().  Global-sort fallback: Tiler::stitch grows T->acc on the host side as before.
+StitchCtx begin_stitch(y3_context* h, Tiler* T, PostProc* P, bool seg, double* preds, y3_mem mem, int64_t cap, const StitchArgs& S) {
+    StitchCtx sc;
+    sc.S = S;
+    T->acc_rows = 0;
+    if (!seg) return sc;
+    sc.cap_rows = std::max<int64_t>(cap, 0);
+    if (mem == Y3_MEM_DEVICE && preds) {
+        sc.preds = preds;
+    } else {
+        T->acc.reserve((size_t)std::max<int64_t>(sc.cap_rows, 1) * 48);
+        sc.preds = T->acc.as<double>();
+    }
+    P->begin_tiled();
+    return sc;
+}
+// stats (optional): receives the control block of the segmented pipeline (candidate / kept totals)
+void finish_stitch(y3_context* h, Tiler* T, PostProc* P, bool seg, double* preds, y3_mem mem, int64_t cap, int64_t* n_out, PostCtrl* stats) {
+    if (seg) {
+        const PostCtrl C = P->finish_tiled();
+        if (stats) *stats = C;
+        Y3_CHECK(!C.any_overflow, Y3_ERR_NOSPACE, "candidate list overflow in a tile batch (raise y3_config.max_candidates)");
+        *n_out = (int64_t)C.acc_rows;
+        Y3_CHECK(C.acc_rows <= cap, Y3_ERR_NOSPACE, "output capacity %lld < %lld boxes", (long long)cap, (long long)C.acc_rows);
+        if (C.acc_rows && !(mem == Y3_MEM_DEVICE && preds)) {
+            Y3_CHECK(preds, Y3_ERR_INVALID, "NULL output");
+            from_device(h, preds, mem, T->acc.p, (size_t)C.acc_rows * 48);
+        }
+        Y3_CUDA(cudaStreamSynchronize(h->stream));
+        return;
+    }
     *n_out = T->acc_rows;
     Y3_CHECK(T->acc_rows <= cap, Y3_ERR_NOSPACE, "output capacity %lld < %lld boxes", (long long)cap, (long long)T->acc_rows);
     if (T->acc_rows) {
@@ -600,13 +598,20 @@ y3_status y3_stitch_tiles(y3_handle h, const float* dets, y3_mem dets_mem, int64
         StitchArgs S{H, W, th, tw, edge};
         // bounded batches so the candidate scratch stays small
         const int64_t step = std::max<int64_t>(1, std::min<int64_t>(count, (int64_t)(64ll << 20) / (int64_t)per_tile));
+        const bool seg = PostProc::segmented_ok(dets_source(nullptr, n_per_tile, 1, nc, true, min_box, score_thr)) && !getenv("Y3_NMS_GLOBAL_SORT");
+        StitchCtx sc = begin_stitch(h, T, P, seg, preds, preds_mem, cap, S);
         for (int64_t t0 = 0; t0 < count; t0 += step) {
             const int64_t nt = std::min(step, count - t0);
             const float* d = static_cast<const float*>(to_device(h, dets + (size_t)t0 * per_tile, dets_mem, (size_t)nt * per_tile * 4, T->dets));
-            NmsResult R = P->run(dets_source(d, n_per_tile, (int)nt, nc, true, min_box, score_thr), iou_thr);
-            T->stitch(P, R, d_geo + first + t0, S);
+            const CandSource src = dets_source(d, n_per_tile, (int)nt, nc, true, min_box, score_thr);
+            sc.geo = d_geo + first + t0;
+            if (!seg || !P->run_tiled(src, iou_thr, sc)) {
+                NmsResult R = P->run(src, iou_thr);
+                T->stitch(P, R, d_geo + first + t0, S);
+            }
         }
-        deliver_preds(h, T, preds, preds_mem, cap, n_out);
+        finish_stitch(h, T, P, seg, preds, preds_mem, cap, n_out, nullptr);
+        flush_phases(h);
     }
     Y3_API_END(h)
 }
@@ -650,6 +655,8 @@ y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dt, y3_mem img_m
         cudaEvent_t ready = upload_rows_until(h, U, rows_needed(0));
         StitchArgs S{H, W, th, tw, edge};
         const int B = net->maxB;
+        const bool seg = PostProc::segmented_ok(heads_source(net, 1, true, min_box, score_thr)) && !getenv("Y3_NMS_GLOBAL_SORT");
+        StitchCtx sc = begin_stitch(h, T, P, seg, preds, preds_mem, cap, S);     // (main stream: ordered before every post-stream run)
         T->tiles.reserve((size_t)B * C * th * tw * 4);
         T->sums.reserve((size_t)B * 16);
         T->dbg_loop = 0.f;
@@ -667,12 +674,16 @@ y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dt, y3_mem img_m
                 h->stream = h->post_stream;                    // every helper enqueues on ctx->stream
             }
             try {
-                NmsResult R;
-                { Phase p(h, &Tm.ms_nms);
-                  R = P->run(heads_source(net, nb, true, min_box, score_thr, set), iou_thr);
-                  p.stop(); Tm.ms_decode += P->last_cand_ms; }
-                Tm.candidates += R.n_cand; Tm.kept += R.n_kept;
-                { Phase p(h, &Tm.ms_stitch); T->stitch(P, R, d_geo + tile_first + t0, S); p.stop(); }
+                const CandSource src = heads_source(net, nb, true, min_box, score_thr, set);
+                sc.geo = d_geo + tile_first + t0;
+                bool done;
+                { Phase p(h, &Tm.ms_nms); done = seg && P->run_tiled(src, iou_thr, sc); p.stop(); }     // no host synchronisation
+                if (!done) {
+                    NmsResult R;
+                    { Phase p(h, &Tm.ms_nms); R = P->run(src, iou_thr); p.stop(); }
+                    Tm.candidates += R.n_cand; Tm.kept += R.n_kept;
+                    { Phase p(h, &Tm.ms_stitch); T->stitch(P, R, d_geo + tile_first + t0, S); p.stop(); }
+                }
             } catch (...) {
                 h->stream = main_stream;
                 throw;
@@ -713,7 +724,11 @@ y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dt, y3_mem img_m
         for (cudaEvent_t e : heads_ready) h->event_pool.push_back(e);
         loop_phase.stop();
         release_upload(h, U);
-        { Phase p(h, &Tm.ms_d2h); deliver_preds(h, T, preds, preds_mem, cap, n_out); p.stop(); }
+        { Phase p(h, &Tm.ms_d2h);
+          PostCtrl st{};
+          finish_stitch(h, T, P, seg, preds, preds_mem, cap, n_out, &st);
+          if (seg) { Tm.candidates = st.sum_cand; Tm.kept = st.sum_kept_nms; }
+          p.stop(); }
     }
     total.stop();
     flush_phases(h);

@@ -44,6 +44,16 @@ __device__ __forceinline__ float decode_corner(const DecodeArgs& D, const float*
     const float half = __fdiv_rn(wh, 2.0f);
     return (k < 2) ? __fsub_rn(c, half) : __fadd_rn(c, half);
 }
+// all four corners of one row at once (the same operations as four decode_corner calls, each evaluated once)
+__device__ __forceinline__ float4 decode_box(const DecodeArgs& D, const float* hp, int s, int cell, int a) {
+    const float tx = __ldg(hp + 0), ty = __ldg(hp + 1), tw = __ldg(hp + 2), th = __ldg(hp + 3);
+    const int gi = cell / D.gw[s], gj = cell - gi * D.gw[s];
+    const float cx = __fmul_rn(__fadd_rn(sigmoid_f(tx), (float)gj), D.stride_h[s]);
+    const float cy = __fmul_rn(__fadd_rn(sigmoid_f(ty), (float)gi), D.stride_w[s]);
+    const float hw = __fdiv_rn(__fmul_rn(expf(tw), D.anchor_w[a]), 2.0f);
+    const float hh = __fdiv_rn(__fmul_rn(expf(th), D.anchor_h[a]), 2.0f);
+    return make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+}
 #endif
 
 void launch_stem(y3_context* ctx, const float* in, __nv_bfloat16* out, const float* w, const float* bias,

@@ -107,6 +107,42 @@ inline void count_launch(y3_context* c, int n = 1) { c->kernels_launched += n; }
         ::y3::count_launch((ctx));      \
     } while (0)
 
+// ---- stage timers: event pairs recorded on the current stream, resolved once at the end of an API call
+inline cudaEvent_t take_event(y3_context* c) {
+    if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    Y3_CUDA(cudaEventCreate(&e));
+    return e;
+}
+// Times a stage with two events on ctx->stream (whatever stream that is when start / stop run); nothing blocks
+// until flush_phases().
+struct Phase {
+    y3_context* c;
+    cudaEvent_t a;
+    float* dst;
+    bool open = true;
+    Phase(y3_context* ctx, float* d) : c(ctx), a(take_event(ctx)), dst(d) { cudaEventRecord(a, c->stream); }
+    void stop() {
+        if (!open) return;
+        open = false;
+        cudaEvent_t b = take_event(c);
+        cudaEventRecord(b, c->stream);
+        c->phase_log.push_back({a, b, dst});
+    }
+    ~Phase() { if (open) c->event_pool.push_back(a); }
+};
+inline void flush_phases(y3_context* c) {
+    cudaStreamSynchronize(c->stream);
+    for (auto& r : c->phase_log) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) *r.dst += t;
+        c->event_pool.push_back(r.a);
+        c->event_pool.push_back(r.b);
+    }
+    c->phase_log.clear();
+    cudaGetLastError();
+}
+
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 static inline int ilog2_ceil(uint64_t v) { int b = 0; while ((1ull << b) < v) ++b; return b; }
 
@@ -141,6 +177,33 @@ __device__ __forceinline__ bool suppresses_exact(const float4 a, const float are
     const float inter = __fmul_rn(dh, dw);
     const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
     if (inter == 0.0f) return !((uni != 0.0f) && (uni == uni) && (0.0f <= thr));
+    return !(__fdiv_rn(inter, uni) <= thr);
+}
+// The same decision without the NaN-propagating selects and - outside a narrow band around the threshold - without
+// the division, for a pair whose coordinates and areas are all finite (box_is_plain) and 0 < thr < inf:
+//   RN(inter / uni) > thr  is certain when  inter > RN(RN(thr * uni) * (1 + 2^-20)),
+//   RN(inter / uni) <= thr is certain when  inter < RN(RN(thr * uni) * (1 - 2^-20))
+// (three roundings of relative size 2^-24 against a margin of 2^-20); anything else takes the exact path.
+__device__ __forceinline__ bool box_is_plain(const float4 b, const float area) {
+    const float inf = __int_as_float(0x7f800000);
+    return fabsf(b.x) < inf && fabsf(b.y) < inf && fabsf(b.z) < inf && fabsf(b.w) < inf && fabsf(area) < inf;
+}
+__device__ __forceinline__ bool suppresses_plain(const float4 a, const float area_a, const float4 b, const float area_b,
+                                                 const float thr) {
+    const float xl = fmaxf(a.x, b.x);
+    const float yt = fmaxf(a.y, b.y);
+    const float xr = fminf(a.z, b.z);
+    const float yb = fminf(a.w, b.w);
+    const float dh = fmaxf(__fsub_rn(yb, yt), 0.0f);
+    const float dw = fmaxf(__fsub_rn(xr, xl), 0.0f);
+    const float inter = __fmul_rn(dh, dw);
+    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    if (inter == 0.0f) return !((uni != 0.0f) && (uni == uni) && (0.0f <= thr));
+    if (uni > 1e-30f && uni < 1e30f && inter > 1e-30f && inter < 1e30f) {
+        const float t = __fmul_rn(thr, uni);
+        if (inter > __fmul_rn(t, 1.00000095367431640625f)) return true;
+        if (inter < __fmul_rn(t, 0.99999904632568359375f)) return false;
+    }
     return !(__fdiv_rn(inter, uni) <= thr);
 }
 __device__ __forceinline__ float box_area_exact(const float4 b) {

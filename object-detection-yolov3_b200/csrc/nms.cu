@@ -22,7 +22,7 @@
 //                     segments, so that the apply phase uses the whole GPU
 //   k_count / k_scan / k_scatter  ordered compaction of the keep flags into the output arrays
 // The n x n/64 bitmask is never materialised in HBM.
-#include "postproc.cuh"
+#include "nms_common.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -30,35 +30,54 @@
 
 namespace y3 {
 
-static constexpr int NMS_T = 512;             // boxes per chunk
-static constexpr int NMS_W = NMS_T / 64;      // mask words per row
-static constexpr int NMS_THREADS = 1024;    // mask + apply phases scale with threads; the sweep is one thread
-static constexpr int64_t BIG_SEGMENT = 32768; // segments above this use resolve/apply launches (whole GPU per segment)
-
-// ------------------------------------------------------------------------------------------
-// orderable score bits: ascending unsigned order == ascending float order
-__device__ __forceinline__ uint32_t orderable(float s) {
-    const uint32_t u = __float_as_uint(s);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float from_orderable(uint32_t o) {
-    const uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
-    return __uint_as_float(u);
-}
-
-struct KeyLayout {
-    int row_bits, seg_shift, total_bits;
-    uint64_t row_mask;
-    // score field = ~orderable(score) - score_base in score_bits bits: scores known to lie in [thr, 1] (the fused
-    // sqrt(sigmoid*sigmoid) path) need 25 bits instead of 32 => one radix pass less
-    uint32_t score_base, score_mask;
+// Where the candidates go.  seg_cnt / slot (optional) feed the segmented pipeline (nms_seg.cu): every candidate also
+// takes the next slot of its (image, class) segment, so that one scan + one scatter bin the list by segment.
+struct CandOut {
+    uint64_t* keys;
+    uint32_t* vals;
+    unsigned long long* counter;
+    int64_t cap;
+    int* seg_cnt;
+    uint32_t* slot;
 };
 
+// All 32 lanes call this (converged); lanes with `pass` append (key, val).  One atomic per warp for the list position
+// and one per distinct segment among the passing lanes (match-any aggregation) for the slot.
+__device__ __forceinline__ void emit_candidates(const CandOut& O, bool pass, uint64_t key, uint32_t val, uint32_t seg, int lane) {
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (!m) return;
+    unsigned long long base = 0;
+    const int leader = __ffs(m) - 1;
+    if (lane == leader) base = atomicAdd(O.counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pass) {
+        const int64_t pos = (int64_t)base + __popc(m & ((1u << lane) - 1u));
+        uint32_t sl = 0;
+        if (O.seg_cnt) {
+            const unsigned peers = __match_any_sync(m, seg);
+            const int l2 = __ffs(peers) - 1;
+            int b2 = 0;
+            if (lane == l2) b2 = atomicAdd(O.seg_cnt + seg, __popc(peers));
+            b2 = __shfl_sync(peers, b2, l2);
+            sl = (uint32_t)(b2 + __popc(peers & ((1u << lane) - 1u)));
+        }
+        if (pos < O.cap) {
+            O.keys[pos] = key;
+            O.vals[pos] = val;
+            if (O.slot) O.slot[pos] = sl;
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t make_key(const KeyLayout& kl, uint64_t seg, float s, uint32_t row) {
+    return (seg << kl.seg_shift) | ((uint64_t)(~orderable(s) - kl.score_base) << kl.row_bits) | (uint64_t)row;
+}
+
+// One thread per (row, class) of decoded rows (or of raw heads: the pre-round-2 form, kept for A/B).
 // IDX = uint32_t when the element count fits (the common case): 64-bit divisions are ~10x slower
 template <typename IDX>
 __global__ void __launch_bounds__(256)
-k_candidates(CandSource src, KeyLayout kl, int64_t total, float logit_floor, uint64_t* __restrict__ keys,
-             uint32_t* __restrict__ vals, unsigned long long* __restrict__ counter, int64_t cap) {
+k_candidates(CandSource src, KeyLayout kl, int64_t total, float logit_floor, CandOut O) {
     const IDX stride = (IDX)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
     // total is rounded up to a multiple of 32 by the loop bound so that ballots stay converged
@@ -68,7 +87,7 @@ k_candidates(CandSource src, KeyLayout kl, int64_t total, float logit_floor, uin
     for (IDX e = (IDX)blockIdx.x * blockDim.x + threadIdx.x; e < total_r; e += stride) {
         bool pass = false;
         uint64_t key = 0;
-        uint32_t val = 0;
+        uint32_t val = 0, seg = 0;
         if (e < (IDX)total) {
             const IDX grow = e / nc;                         // global row = img * rows + row
             const int c = (int)(e - grow * nc);
@@ -111,93 +130,155 @@ k_candidates(CandSource src, KeyLayout kl, int64_t total, float logit_floor, uin
                 }
             }
             if (pass) {
-                const uint64_t seg = (uint64_t)img * src.nc + (uint64_t)c;
-                key = (seg << kl.seg_shift) | ((uint64_t)(~orderable(s) - kl.score_base) << kl.row_bits) | (uint64_t)row;
+                seg = (uint32_t)((uint64_t)img * src.nc + (uint64_t)c);
+                key = make_key(kl, seg, s, (uint32_t)row);
                 val = (uint32_t)grow;
             }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m) {
-            unsigned long long base = 0;
-            const int leader = __ffs(m) - 1;
-            if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (pass) {
-                const int64_t pos = (int64_t)base + __popc(m & ((1u << lane) - 1u));
-                if (pos < cap) { keys[pos] = key; vals[pos] = val; }
-            }
-        }
+        emit_candidates(O, pass, key, val, seg, lane);
     }
 }
 
-// Fused decode + threshold + compaction straight from the raw fp32 heads, organised by ROW: L = 1..32 lanes share
-// one output row (L = smallest power of two >= NC, capped at 32), so the row's address arithmetic, its objectness
-// logit and - only when needed - its box are computed once per row instead of once per (row, class), the class
-// logits of a row are read by neighbouring lanes (coalesced), and a row whose objectness logit cannot reach the
-// threshold costs ONE 4-byte load (score^2 = obj*cls <= obj).  Same exact arithmetic as k_candidates.
+// Fused decode + threshold + compaction straight from the raw fp32 heads (same exact arithmetic as k_candidates).
+// One lane per row: 32 independent objectness loads in flight per warp; a row whose objectness logit cannot reach the
+// threshold costs this one 4-byte load (score^2 = obj*cls <= obj).
+//   one class   : k_candidates_heads1 - the lane finishes its own row (class logit, score, size filter, emit);
+//   many classes: k_live_rows appends the rows that can still pass to a list, k_candidates_rows then gives every
+//                 listed row to ONE WARP (grid-stride over the device-side list length): the 32 lanes read the row's
+//                 class logits side by side, ONE atomic reserves the row's list positions and every passing class takes
+//                 its segment slot with an independent atomic.  (Round 1 walked rows in place: the rows that pass
+//                 cluster spatially, so a few warps did most of the work serially - 18 % warps active, 0.10 ms on K2.)
 __global__ void __launch_bounds__(256)
-k_candidates_heads(CandSource src, KeyLayout kl, int lanes_per_row_log2, float logit_floor, uint64_t* __restrict__ keys,
-                   uint32_t* __restrict__ vals, unsigned long long* __restrict__ counter, int64_t cap) {
+k_candidates_heads1(CandSource src, KeyLayout kl, float logit_floor, CandOut O) {
     const int lane = threadIdx.x & 31;
-    const int L = 1 << lanes_per_row_log2;
-    const int sub = lane & (L - 1);                    // this lane's first class
-    const int rows_per_warp = 32 >> lanes_per_row_log2;
     const uint32_t rpi = (uint32_t)src.rows_per_image;
     const uint32_t rows_total = rpi * (uint32_t)src.n_images;
     const uint32_t warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    const int nc = src.nc;
-    const int iters = (nc + L - 1) >> lanes_per_row_log2;
     const float thr = src.score_thr;
-    for (uint32_t base = warp_g * rows_per_warp; base < rows_total; base += n_warps * rows_per_warp) {
-        const uint32_t grow = base + (uint32_t)(lane >> lanes_per_row_log2);
-        const bool valid = grow < rows_total;
+    for (uint32_t base = warp_g * 32u; base < rows_total; base += n_warps * 32u) {
+        const uint32_t grow = base + (uint32_t)lane;
+        bool pass = false;
+        float s = 0.f;
         uint32_t img = 0, row = 0;
-        int sc = 0, cell = 0, a = 0;
-        const float* hp = nullptr;
-        float lo = -INFINITY;
-        if (valid) {
+        if (grow < rows_total) {
             img = grow / rpi;
             row = grow - img * rpi;
-            hp = head_row(src.dec, (int)img, (int)row, &sc, &cell, &a);
-            lo = __ldg(hp + 4);
-        }
-        const bool live = valid && (lo >= logit_floor);
-        if (!__any_sync(0xffffffffu, live)) continue;
-        const float o = live ? sigmoid_f(lo) : 0.f;
-        bool size_known = !src.filter_small, size_ok = true;
-        for (int it = 0; it < iters; ++it) {
-            const int c = sub + (it << lanes_per_row_log2);
-            bool pass = false;
-            float s = 0.f;
-            if (live && c < nc) {
-                const float lc = __ldg(hp + 5 + c);
+            int sc, cell, a;
+            const float* hp = head_row(src.dec, (int)img, (int)row, &sc, &cell, &a);
+            const float lo = __ldg(hp + 4);
+            if (lo >= logit_floor) {
+                const float lc = __ldg(hp + 5);
                 if (lc >= logit_floor) {
-                    s = __fsqrt_rn(__fmul_rn(sigmoid_f(lc), o));
+                    s = __fsqrt_rn(__fmul_rn(sigmoid_f(lc), sigmoid_f(lo)));
                     pass = (s >= thr);
-                    if (pass && !size_known) {
+                    if (pass && src.filter_small) {
                         const float w = __fsub_rn(decode_corner(src.dec, hp, sc, cell, a, 2), decode_corner(src.dec, hp, sc, cell, a, 0));
                         const float h = __fsub_rn(decode_corner(src.dec, hp, sc, cell, a, 3), decode_corner(src.dec, hp, sc, cell, a, 1));
-                        size_ok = (w > src.min_size) && (h > src.min_size);
-                        size_known = true;
+                        pass = (w > src.min_size) && (h > src.min_size);
                     }
-                    pass = pass && size_ok;
                 }
             }
-            const unsigned m = __ballot_sync(0xffffffffu, pass);
-            if (m) {
-                unsigned long long b0 = 0;
-                const int leader = __ffs(m) - 1;
-                if (lane == leader) b0 = atomicAdd(counter, (unsigned long long)__popc(m));
-                b0 = __shfl_sync(0xffffffffu, b0, leader);
-                if (pass) {
-                    const int64_t pos = (int64_t)b0 + __popc(m & ((1u << lane) - 1u));
-                    if (pos < cap) {
-                        const uint64_t seg = (uint64_t)img * (uint64_t)nc + (uint64_t)c;
-                        keys[pos] = (seg << kl.seg_shift) | ((uint64_t)(~orderable(s) - kl.score_base) << kl.row_bits) | (uint64_t)row;
-                        vals[pos] = grow;
+        }
+        emit_candidates(O, pass, make_key(kl, img, s, row), grow, img, lane);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_live_rows(CandSource src, float logit_floor, uint32_t* __restrict__ live, unsigned int* __restrict__ n_live) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t rpi = (uint32_t)src.rows_per_image;
+    const uint32_t rows_total = rpi * (uint32_t)src.n_images;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rows_r = (rows_total + 31u) & ~31u;
+    for (uint32_t grow = blockIdx.x * blockDim.x + threadIdx.x; grow < rows_r; grow += stride) {
+        bool alive = false;
+        if (grow < rows_total) {
+            const uint32_t img = grow / rpi;
+            int sc, cell, a;
+            const float* hp = head_row(src.dec, (int)img, (int)(grow - img * rpi), &sc, &cell, &a);
+            alive = __ldg(hp + 4) >= logit_floor;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, alive);
+        if (m) {
+            unsigned base = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) base = atomicAdd(n_live, (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (alive) live[base + __popc(m & ((1u << lane) - 1u))] = grow;
+        }
+    }
+}
+
+static constexpr int ROW_IT = 4;     // class chunks of 32 handled per emission group (128 classes)
+
+__global__ void __launch_bounds__(256)
+k_candidates_rows(CandSource src, KeyLayout kl, float logit_floor, const uint32_t* __restrict__ live,
+                  const unsigned int* __restrict__ n_live, CandOut O) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t rpi = (uint32_t)src.rows_per_image;
+    const uint32_t warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int nc = src.nc;
+    const float thr = src.score_thr;
+    const uint32_t n = *n_live;
+    for (uint32_t li = warp_g; li < n; li += n_warps) {
+        const uint32_t grow = live[li];
+        const uint32_t img = grow / rpi, row = grow - img * rpi;
+        int sc, cell, a;
+        const float* hp = head_row(src.dec, (int)img, (int)row, &sc, &cell, &a);
+        const float o = sigmoid_f(__ldg(hp + 4));
+        bool size_known = !src.filter_small, size_ok = true;
+        for (int c00 = 0; c00 < nc; c00 += 32 * ROW_IT) {
+            float lc[ROW_IT];
+#pragma unroll
+            for (int it = 0; it < ROW_IT; ++it) {
+                const int c = c00 + it * 32 + lane;
+                lc[it] = (c < nc) ? __ldg(hp + 5 + c) : -INFINITY;
+            }
+            float s[ROW_IT];
+            unsigned pm[ROW_IT];
+            bool any = false;
+#pragma unroll
+            for (int it = 0; it < ROW_IT; ++it) {
+                s[it] = 0.f;
+                bool p = false;
+                if (lc[it] >= logit_floor) {
+                    s[it] = __fsqrt_rn(__fmul_rn(sigmoid_f(lc[it]), o));
+                    p = (s[it] >= thr);
+                }
+                pm[it] = __ballot_sync(0xffffffffu, p);
+                any |= pm[it] != 0;
+            }
+            if (!any) continue;
+            if (!size_known) {                                   // warp-uniform: every lane evaluates the same box
+                const float w = __fsub_rn(decode_corner(src.dec, hp, sc, cell, a, 2), decode_corner(src.dec, hp, sc, cell, a, 0));
+                const float h = __fsub_rn(decode_corner(src.dec, hp, sc, cell, a, 3), decode_corner(src.dec, hp, sc, cell, a, 1));
+                size_ok = (w > src.min_size) && (h > src.min_size);
+                size_known = true;
+            }
+            if (!size_ok) break;                                 // the whole row is dropped by filter_small_boxes
+            int total = 0;
+#pragma unroll
+            for (int it = 0; it < ROW_IT; ++it) total += __popc(pm[it]);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(O.counter, (unsigned long long)total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            int before = 0;
+#pragma unroll
+            for (int it = 0; it < ROW_IT; ++it) {
+                if ((pm[it] >> lane) & 1u) {
+                    const uint32_t seg = img * (uint32_t)nc + (uint32_t)(c00 + it * 32 + lane);
+                    const int64_t pos = (int64_t)base + before + __popc(pm[it] & ((1u << lane) - 1u));
+                    uint32_t sl = 0;
+                    if (O.seg_cnt) sl = (uint32_t)atomicAdd(O.seg_cnt + seg, 1);      // classes of one row: all segments differ
+                    if (pos < O.cap) {
+                        O.keys[pos] = make_key(kl, seg, s[it], row);
+                        O.vals[pos] = grow;
+                        if (O.slot) O.slot[pos] = sl;
                     }
                 }
+                before += __popc(pm[it]);
             }
         }
     }
@@ -343,83 +424,6 @@ k_rs_scatter(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin,
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// One chunk (<= NMS_T boxes starting at `base`) of one segment: build the IoU bitmask in shared
-// memory, sweep it serially, return the kept local indices in s_klist / s_nk.
-struct ChunkSmem {
-    float4 box[NMS_T];
-    float area[NMS_T];
-    unsigned long long mask[NMS_T * NMS_W];
-    unsigned long long dead[NMS_W];
-    int klist[NMS_T];
-    int nk;
-};
-
-// idx (optional, shared memory): the chunk is the gathered boxes sbox[base + idx[j]] (all alive) instead of the
-// contiguous run sbox[base + j]
-__device__ __forceinline__ void chunk_resolve(ChunkSmem& S, const float4* __restrict__ sbox,
-                                              const float* __restrict__ sarea,
-                                              const uint8_t* __restrict__ supp, int64_t base, int ct, float thr,
-                                              const int* idx = nullptr) {
-    const int tid = threadIdx.x;
-    // load + dead bits (already suppressed by earlier chunks, or past the end)
-    uint32_t* dead32 = reinterpret_cast<uint32_t*>(S.dead);
-    for (int j = tid; j < NMS_T; j += NMS_THREADS) {
-        bool dead = true;
-        if (j < ct) {
-            const int64_t e = base + (idx ? idx[j] : j);
-            S.box[j] = sbox[e];
-            S.area[j] = sarea[e];
-            dead = idx ? false : (supp[e] != 0);
-        }
-        const unsigned b = __ballot_sync(0xffffffffu, dead);
-        if ((tid & 31) == 0) dead32[j >> 5] = b;
-    }
-    __syncthreads();
-    // bitmask: lanes walk rows i, all lanes of a warp share the word w => box j is a broadcast read
-    const int nw = (ct + 63) >> 6;
-    for (int idx = tid; idx < NMS_T * nw; idx += NMS_THREADS) {
-        const int w = idx / NMS_T;
-        const int i = idx - w * NMS_T;
-        if (i >= ct || w < (i >> 6)) continue;
-        if ((S.dead[i >> 6] >> (i & 63)) & 1ull) continue;          // row never read by the sweep
-        const float4 bi = S.box[i];
-        const float ai = S.area[i];
-        unsigned long long bits = 0;
-        const int j0 = w << 6;
-        const int jn = min(64, ct - j0);
-        for (int b = 0; b < jn; ++b) {
-            const int j = j0 + b;
-            if (j > i && suppresses_exact(bi, ai, S.box[j], S.area[j], thr)) bits |= (1ull << b);
-        }
-        S.mask[i * NMS_W + w] = bits;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        unsigned long long dead[NMS_W];
-#pragma unroll
-        for (int w = 0; w < NMS_W; ++w) dead[w] = S.dead[w];
-        int nk = 0;
-#pragma unroll
-        for (int w0 = 0; w0 < NMS_W; ++w0) {
-            unsigned long long cur = ~dead[w0];
-            while (cur) {
-                const int b = __ffsll((long long)cur) - 1;
-                const int i = (w0 << 6) + b;
-                S.klist[nk++] = i;
-                const unsigned long long* row = S.mask + i * NMS_W;
-#pragma unroll
-                for (int w = 0; w < NMS_W; ++w)
-                    if (w >= w0) dead[w] |= row[w];
-                const unsigned long long above = (b == 63) ? 0ull : (~0ull << (b + 1));
-                cur = ~dead[w0] & above;
-            }
-        }
-        S.nk = nk;
-    }
-    __syncthreads();
-}
-
 // Segments of at most 256 boxes (the many-class regime: K2 has 5120 segments of ~50 boxes): one WARP per segment,
 // PL boxes per lane (box j lives in slot j / 32 of lane j % 32), the alive set is PL 32-bit masks that every lane keeps
 // in step through ballots.  Same greedy order and the same exact suppression test as the chunk path.
@@ -478,38 +482,6 @@ k_nms_small(const float4* __restrict__ sbox, const float* __restrict__ sarea, ui
         else if (m <= 128) warp_nms<4>(sbox, sarea, keepf, s0, m, thr, lane);
         else warp_nms<8>(sbox, sarea, keepf, s0, m, thr, lane);
     }
-}
-
-// Gathers (in order) the indices of the next <= NMS_T still-alive boxes of a segment behind *s_pos into s_idx and
-// advances *s_pos past the last position examined.  All NMS_THREADS threads call it; returns the count.
-__device__ __forceinline__ int gather_alive(const uint8_t* __restrict__ supp, int64_t s0, long long m, long long* s_pos, int* s_n,
-                                            int* s_idx, int* s_wcount) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) *s_n = 0;
-    __syncthreads();
-    while (true) {
-        const long long pos = *s_pos;
-        const int have = *s_n;
-        if (pos >= m || have >= NMS_T) break;
-        const long long p = pos + threadIdx.x;
-        const bool alive = p < m && supp[s0 + p] == 0;
-        const unsigned b = __ballot_sync(0xffffffffu, alive);
-        if (lane == 0) s_wcount[wid] = __popc(b);
-        __syncthreads();
-        int before = 0, total = 0;
-        for (int w = 0; w < NMS_THREADS / 32; ++w) { const int c = s_wcount[w]; if (w < wid) before += c; total += c; }
-        const int rank = have + before + __popc(b & ((1u << lane) - 1u));
-        if (alive && rank < NMS_T) s_idx[rank] = (int)p;
-        // positions consumed: the whole window if everything fitted, else up to the alive box that took the last slot
-        __syncthreads();
-        if (have + total <= NMS_T) {
-            if (threadIdx.x == 0) { *s_n = have + total; *s_pos = min(pos + (long long)NMS_THREADS, m); }
-        } else {
-            if (alive && rank == NMS_T - 1) { *s_n = NMS_T; *s_pos = p + 1; }
-        }
-        __syncthreads();
-    }
-    return *s_n;
 }
 
 __global__ void __launch_bounds__(NMS_THREADS)
@@ -729,14 +701,8 @@ int64_t PostProc::flag_offsets(const uint8_t* flags, int64_t n) {
     return (int64_t)h[1];
 }
 
-NmsResult PostProc::run(const CandSource& src, float iou_thr) {
-    cudaStream_t st = ctx->stream;
-    NmsResult R;
-    const int64_t rows = src.rows_per_image * src.n_images;
-    const int64_t total = rows * src.nc;
-    if (total <= 0) return R;
+KeyLayout PostProc::key_layout(const CandSource& src) const {
     const int64_t nseg64 = (int64_t)src.n_images * src.nc;
-    Y3_CHECK(rows < (1ll << 32), Y3_ERR_UNSUPPORTED, "too many rows (%lld)", (long long)rows);
     KeyLayout kl;
     kl.row_bits = ilog2_ceil((uint64_t)src.rows_per_image);
     if (kl.row_bits == 0) kl.row_bits = 1;
@@ -758,53 +724,124 @@ NmsResult PostProc::run(const CandSource& src, float iou_thr) {
     kl.total_bits = kl.seg_shift + seg_bits;
     kl.row_mask = (1ull << kl.row_bits) - 1ull;
     Y3_CHECK(kl.total_bits <= 64, Y3_ERR_UNSUPPORTED, "sort key needs %d bits", kl.total_bits);
-    const int nseg = (int)nseg64;
+    return kl;
+}
 
-    int64_t cap = ctx->cfg.max_candidates > 0 ? ctx->cfg.max_candidates : total;
-    if (cap > total) cap = total;
-    keys[0].reserve(cap * 8); keys[1].reserve(cap * 8);
-    vals[0].reserve(cap * 4); vals[1].reserve(cap * 4);
+// Capacity of the candidate list: y3_config.max_candidates, else every (row, class) pair up to 4 Mi entries and never
+// fewer than the rows (so that a single class can always pass completely).
+int64_t PostProc::capacity(const CandSource& src) const {
+    const int64_t rows = src.rows_per_image * src.n_images;
+    const int64_t total = rows * src.nc;
+    int64_t cap = ctx->cfg.max_candidates > 0 ? ctx->cfg.max_candidates : std::min<int64_t>(total, std::max<int64_t>(rows, 4ll << 20));
+    return std::min(cap, total);
+}
+
+// threshold + compaction (+ fused decode) into keys[0] / vals[0]; counters[0] = candidate count (zeroed here)
+void PostProc::launch_candidates(const CandSource& src, const KeyLayout& kl, int64_t cap, bool count_segments) {
+    cudaStream_t st = ctx->stream;
+    const int64_t rows = src.rows_per_image * src.n_images;
+    const int64_t total = rows * src.nc;
+    keys[0].reserve(cap * 8);
+    vals[0].reserve(cap * 4);
     counters.reserve(64);
-    host_small.reserve(64 + (size_t)(nseg + 1) * 8);
     Y3_CUDA(cudaMemsetAsync(counters.p, 0, 64, st));
-
-    {
-        // logit(thr^2) minus a margin far above any rounding of expf / the division (see k_candidates)
-        float logit_floor = -INFINITY;
-        if (src.from_heads && src.score_thr > 0.f && src.score_thr < 1.f) {
-            const double t2 = (double)src.score_thr * (double)src.score_thr;
-            logit_floor = (float)(log(t2 / (1.0 - t2)) - 0.05);
-        }
-        const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
-        if (!ev0) { Y3_CUDA(cudaEventCreate(&ev0)); Y3_CUDA(cudaEventCreate(&ev1)); }
-        Y3_CUDA(cudaEventRecord(ev0, st));
-        static const bool row_kernel = getenv("Y3_CAND_OLD") == nullptr;
-        if (row_kernel && src.from_heads && total + 32 < (1ll << 32)) {
-            int l2 = 0;
-            while ((1 << l2) < src.nc && l2 < 5) ++l2;
-            const int64_t rows_total = src.rows_per_image * src.n_images;
-            const int64_t warps = (rows_total + (32 >> l2) - 1) / (32 >> l2);
-            const int rblocks = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)ctx->sm_count * 16);
-            k_candidates_heads<<<rblocks, 256, 0, st>>>(src, kl, l2, logit_floor, keys[0].as<uint64_t>(), vals[0].as<uint32_t>(),
-                                                         counters.as<unsigned long long>(), cap);
-        } else if (total + 32 < (1ll << 32))
-            k_candidates<uint32_t><<<blocks, 256, 0, st>>>(src, kl, total, logit_floor, keys[0].as<uint64_t>(), vals[0].as<uint32_t>(),
-                                                           counters.as<unsigned long long>(), cap);
-        else
-            k_candidates<uint64_t><<<blocks, 256, 0, st>>>(src, kl, total, logit_floor, keys[0].as<uint64_t>(), vals[0].as<uint32_t>(),
-                                                           counters.as<unsigned long long>(), cap);
-        Y3_CUDA(cudaEventRecord(ev1, st));
-        Y3_LAUNCHED(ctx);
+    CandOut O{keys[0].as<uint64_t>(), vals[0].as<uint32_t>(), counters.as<unsigned long long>(), cap, nullptr, nullptr};
+    if (count_segments) {
+        slot.reserve(cap * 4);
+        O.seg_cnt = seg_cnt.as<int>();
+        O.slot = slot.as<uint32_t>();
     }
+    // logit(thr^2) minus a margin far above any rounding of expf / the division (see k_candidates)
+    float logit_floor = -INFINITY;
+    if (src.from_heads && src.score_thr > 0.f && src.score_thr < 1.f) {
+        const double t2 = (double)src.score_thr * (double)src.score_thr;
+        logit_floor = (float)(log(t2 / (1.0 - t2)) - 0.05);
+    }
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
+    static const bool row_kernel = getenv("Y3_CAND_OLD") == nullptr;
+    if (row_kernel && src.from_heads && total + 32 < (1ll << 32)) {
+        const int rblocks = (int)std::min<int64_t>((rows + 255) / 256, (int64_t)ctx->sm_count * 8);
+        if (src.nc == 1) {
+            k_candidates_heads1<<<rblocks, 256, 0, st>>>(src, kl, logit_floor, O);
+        } else {
+            live.reserve((size_t)rows * 4);
+            unsigned int* n_live = reinterpret_cast<unsigned int*>(counters.as<unsigned char>() + 16);     // zeroed above
+            k_live_rows<<<rblocks, 256, 0, st>>>(src, logit_floor, live.as<uint32_t>(), n_live);
+            Y3_LAUNCHED(ctx);
+            k_candidates_rows<<<ctx->sm_count * 8, 256, 0, st>>>(src, kl, logit_floor, live.as<uint32_t>(), n_live, O);
+        }
+    } else if (total + 32 < (1ll << 32)) {
+        k_candidates<uint32_t><<<blocks, 256, 0, st>>>(src, kl, total, logit_floor, O);
+    } else {
+        k_candidates<uint64_t><<<blocks, 256, 0, st>>>(src, kl, total, logit_floor, O);
+    }
+    Y3_LAUNCHED(ctx);
+}
+
+void PostProc::enqueue(const CandSource& src, float iou_thr) {
+    cudaStream_t st = ctx->stream;
+    pending = NmsResult();
+    pending_cap = -1;
+    const int64_t rows = src.rows_per_image * src.n_images;
+    const int64_t total = rows * src.nc;
+    if (total <= 0) return;
+    Y3_CHECK(rows < (1ll << 32), Y3_ERR_UNSUPPORTED, "too many rows (%lld)", (long long)rows);
+    const KeyLayout kl = key_layout(src);
+    const int64_t cap = capacity(src);
+    static const bool no_seg = getenv("Y3_NMS_GLOBAL_SORT") != nullptr;      // A/B: the round-1 global-sort pipeline only
+    if (!no_seg && (int64_t)src.n_images * src.nc < (1ll << 24) && kl.seg_shift <= 62) {
+        // segmented pipeline: bin by (image, class), per-segment NMS.  Segments are bounded by rows_per_image; when that
+        // bound exceeds what one CTA sorts in shared memory the largest segment is read back before the route is chosen.
+        segmented_front(src, kl, cap);
+        if (segmented_ok(src)) {
+            segmented_nms(src, kl, iou_thr, nullptr);
+            segmented_emit_plain(src, kl);
+            return;
+        }
+        host_ctrl.reserve(sizeof(PostCtrl));
+        Y3_CUDA(cudaMemcpyAsync(host_ctrl.p, ctrl.p, sizeof(PostCtrl), cudaMemcpyDeviceToHost, st));
+        Y3_CUDA(cudaStreamSynchronize(st));
+        const PostCtrl C = *host_ctrl.as<PostCtrl>();
+        Y3_CHECK(!C.overflow, Y3_ERR_NOSPACE, "candidate list overflow: %llu candidates, capacity %lld (raise y3_config.max_candidates)",
+                 C.n_cand, (long long)cap);
+        pending.n_cand = (int64_t)C.n_cand;
+        if (C.K == 0) return;
+        if (C.max_seg <= SEG_MID_MAX) {
+            segmented_nms(src, kl, iou_thr, nullptr);
+            segmented_emit_plain(src, kl);
+            return;
+        }
+        pending = run_global_sort(src, iou_thr, kl, cap, C.K);           // keys[0] / vals[0] hold the unsorted list
+        return;
+    }
+    if (!ev0) { Y3_CUDA(cudaEventCreate(&ev0)); Y3_CUDA(cudaEventCreate(&ev1)); }
+    Y3_CUDA(cudaEventRecord(ev0, st));
+    launch_candidates(src, kl, cap, false);
+    Y3_CUDA(cudaEventRecord(ev1, st));
+    host_small.reserve(64);
     unsigned long long* h_cnt = host_small.as<unsigned long long>();
     Y3_CUDA(cudaMemcpyAsync(h_cnt, counters.p, 8, cudaMemcpyDeviceToHost, st));
     Y3_CUDA(cudaStreamSynchronize(st));
     const int64_t K = (int64_t)h_cnt[0];
-    R.n_cand = K;
-    { float ms = 0.f; if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) last_cand_ms = ms; }
+    { float ms = 0.f; if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) ctx->timings.ms_decode += ms; }
     Y3_CHECK(K <= cap, Y3_ERR_NOSPACE, "candidate list overflow: %lld candidates, capacity %lld "
              "(raise y3_config.max_candidates)", (long long)K, (long long)cap);
-    if (K == 0) return R;
+    pending.n_cand = K;
+    if (K == 0) return;
+    pending = run_global_sort(src, iou_thr, kl, cap, K);
+}
+
+// The round-1 pipeline from the unsorted candidate list on: global radix sort by (segment, score desc, row asc),
+// segment offsets, NMS (whole-GPU apply phase for very large segments), ordered compaction.  Used when a segment can
+// exceed what one CTA sorts in shared memory (e.g. single_class_nms on 200 k boxes).  Synchronises the stream.
+NmsResult PostProc::run_global_sort(const CandSource& src, float iou_thr, const KeyLayout& kl, int64_t cap, int64_t K) {
+    cudaStream_t st = ctx->stream;
+    NmsResult R;
+    R.n_cand = K;
+    const int nseg = (int)((int64_t)src.n_images * src.nc);
+    keys[1].reserve(cap * 8);
+    vals[1].reserve(cap * 4);
+    host_small.reserve(64 + (size_t)(nseg + 1) * 8);
 
     // sort by (segment, score desc, row asc): own stable LSD radix sort over the used key bits
     Y3_CHECK(K < (1ll << 31), Y3_ERR_UNSUPPORTED, "too many candidates (%lld)", (long long)K);

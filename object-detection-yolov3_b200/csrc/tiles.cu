@@ -228,33 +228,10 @@ k_stitch_flags(const float4* __restrict__ boxes, const int32_t* __restrict__ til
                const TileGeo* __restrict__ geo, StitchArgs S, int4* __restrict__ ibox, uint8_t* __restrict__ flags) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4 b = boxes[i];
-    const TileGeo g = geo[tile[i]];
-    const float r = (float)S.edge;
-    const float ox = (float)g.rec_x, oy = (float)g.rec_y;
-    // inference_tiled.py:237-254 (fp32 scalars, python-int operands converted to fp32)
-    const float cx = __fdiv_rn(__fadd_rn(b.z, b.x), 2.0f);
-    const float cy = __fdiv_rn(__fadd_rn(b.w, b.y), 2.0f);
-    const float gx = __fadd_rn(cx, ox);
-    const float gy = __fadd_rn(cy, oy);
-    bool bad = (gy > r) && (cy < r);
-    bad |= (gy <= (float)(S.img_h - S.edge)) && (cy >= (float)(S.tile_h - S.edge));
-    bad |= (gx > r) && (cx < r);
-    bad |= (gx <= (float)(S.img_w - S.edge)) && (cx >= (float)(S.tile_w - S.edge));
-    // :263-266 origin add, :278 np.round -> int32
-    int x0 = (int)rintf(__fadd_rn(b.x, ox));
-    int y0 = (int)rintf(__fadd_rn(b.y, oy));
-    int x1 = (int)rintf(__fadd_rn(b.z, ox));
-    int y1 = (int)rintf(__fadd_rn(b.w, oy));
-    // :281-288 centre must lie inside the image (int32 sum, then / 2.0 in double)
-    const double ccx = (double)(x1 + x0) / 2.0, ccy = (double)(y1 + y0) / 2.0;
-    const bool outside = (ccx < 0) || (ccx >= (double)S.img_w) || (ccy < 0) || (ccy >= (double)S.img_h);
-    // :291-301 clamp
-    const int mw = (int)S.img_w - 1, mh = (int)S.img_h - 1;
-    x0 = min(max(x0, 0), mw); x1 = min(max(x1, 0), mw);
-    y0 = min(max(y0, 0), mh); y1 = min(max(y1, 0), mh);
-    ibox[i] = make_int4(x0, y0, x1, y1);
-    flags[i] = (!bad && !outside) ? 1 : 0;
+    int4 ib;
+    const bool keep = stitch_box(boxes[i], geo[tile[i]], S, &ib);
+    ibox[i] = ib;
+    flags[i] = keep ? 1 : 0;
 }
 
 __global__ void __launch_bounds__(CMP_BLOCK)

@@ -5,17 +5,6 @@
 
 namespace y3 {
 
-struct TileGeo {
-    int y0, y1, x0, x1;     // clamped crop in the image
-    int pre_y, pre_x;       // reflect padding before the crop
-    int rec_x, rec_y;       // origin the reference records (clamped)
-};
-
-struct StitchArgs {
-    int64_t img_h, img_w;
-    int tile_h, tile_w, edge;
-};
-
 std::vector<TileGeo> plan_tiles(int64_t H, int64_t W, int th, int tw, int edge, int* ry, int* rx);
 
 void launch_tile_norm(y3_context* ctx, const void* img_dev, int dtype, long long row_lo, int W, int C,

@@ -52,9 +52,12 @@ def test_multiclass_80_golden(post, golden):
     assert (sha(b), sha(s), sha(l)) == (str(g["mc80_sha_boxes"]), str(g["mc80_sha_scores"]), str(g["mc80_sha_labels"]))
 
 
-@pytest.mark.parametrize("m", [1, 2, 31, 64, 511, 512, 513, 1025, 4096, 8192, 8193, 20000])
+@pytest.mark.parametrize("m", [1, 2, 31, 32, 33, 64, 65, 100, 128, 129, 200, 256, 257, 511, 512, 513, 1025, 4096, 5632, 5633, 8192, 8193,
+                               20000, 24576, 24577, 40000])
 def test_sizes_vs_c_oracle(post, m):
-    """chunk boundaries (512), the big-segment route (> 8192) and tiny inputs"""
+    """every route of the segmented pipeline: one warp per segment (<= 256 boxes, 1 / 2 / 4 / 8 boxes per lane), one CTA with
+    the small (<= 5632) and the large (<= 24576) key buffer, chunk boundaries of the bitmask NMS (512), and the global-sort
+    pipeline above that"""
     b, s = cases.nms_case(m, 40 * np.sqrt(m) + 50, seed=m, wh=(20, 120))
     for thr in (0.3, 0.45):
         assert post.single_class_nms(b, s, thr).tolist() == nms_c.greedy_nms(b, s, thr)

@@ -25,3 +25,13 @@ def test_variant_heads(env):
     errs = json.loads(line[len("RESULT "):])
     print(env, errs)
     assert all(max(v) <= HEAD_TOL for v in errs.values()), errs
+
+
+def test_global_sort_pipeline_variant():
+    """Y3_NMS_GLOBAL_SORT=1: the round-1 post-processing pipeline (global radix sort, host-synchronised) is kept as the route
+    for very large segments and as an A/B switch - the NMS, detect and tiled suites must hold with it, bit for bit."""
+    p = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-k", "not k3_200k",
+                        os.path.join(HERE, "test_gpu_nms.py"), os.path.join(HERE, "test_gpu_tiled_e2e.py"),
+                        os.path.join(HERE, "test_gpu_net.py") + "::test_detect_pipeline_exact_on_own_boxes"],
+                       env=dict(os.environ, Y3_NMS_GLOBAL_SORT="1"), capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]

@@ -1,9 +1,9 @@
 """Per-layer timing of the conv stack on the GPU (measurement helper, not part of the product).
-    python tools_profile_layers.py [H W C NC batch]"""
+    python tools/profile_layers.py [H W C NC batch]"""
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "object-detection-yolov3_b200"))
 from yolo3_b200 import Engine, weights  # noqa: E402
 

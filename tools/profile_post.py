@@ -5,7 +5,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "object-detection-yolov3_b200"))
 import bench  # noqa: E402
@@ -18,5 +18,13 @@ x2 = np.random.default_rng(1).standard_normal((64, 3, 416, 416)).astype(np.float
 bench.calibrate_heads(e2, w2, x2[:8], pass_frac=0.002, nc=80, interior=False)
 e2.detect(x2, bench.MIN_BOX, bench.IOU_THR, bench.SCORE_THR)
 print("MEASURED CALL")
-e2.detect(x2, bench.MIN_BOX, bench.IOU_THR, bench.SCORE_THR)
-print(e2.timings())
+best = None
+for _ in range(5):
+    e2.detect(x2, bench.MIN_BOX, bench.IOU_THR, bench.SCORE_THR)
+    t = e2.timings()
+    if best is None or t["ms_nms"] < best["ms_nms"]:
+        best = t
+print(best)
+nbytes = 64 * 10647 * 85 * 4 + best["candidates"] * 56 + best["kept"] * 4
+print("decode+NMS %.3f ms, %.1f GB/s on the SURVEY 8(d) byte model (%.1f MB), candidates kernel %.3f ms"
+      % (best["ms_nms"], nbytes / best["ms_nms"] / 1e6, nbytes / 1e6, best["ms_decode"]))
