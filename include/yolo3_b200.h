@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define Y3_ABI_VERSION 2   /* 2: + y3_zscore */
+#define Y3_ABI_VERSION 3   /* 2: + y3_zscore; 3: + y3_comm_*, y3_infer_tiled_sharded, y3_cross_seam_nms, y3_timings.ms_comm */
 #define Y3_MAX_ANCHORS 8
 
 typedef int32_t y3_status;
@@ -114,6 +114,16 @@ y3_status y3_detect(y3_handle h, const float* in_nchw, y3_mem in_mem, int32_t ba
                     int32_t* out_labels /*[cap]*/, int32_t* out_img_index /*[cap]*/,
                     int64_t cap, int64_t* n_out);
 
+/* replaces: the per-image body of inference.inference (inference.py:47-79) in ONE call: astype(float32) ->
+ * imagereader.zscore_normalize over the whole image -> HWC->NCHW -> yolo_model(batch) -> clip of the corners to the image
+ * (clip != 0; inference.py:62-65 as intended: x to [0, W], y to [0, H]) -> filter_small_boxes -> per_class_nms.
+ * img: HWC, H x W x C = the network input size, any y3_dtype, host|device.  Outputs in the reference's order
+ * (class-major, score-descending), not yet converted to x,y,w,h.  The batch-1 forward replays a CUDA graph. */
+y3_status y3_detect_image(y3_handle h, const void* img, y3_dtype dtype, y3_mem img_mem, int32_t img_h, int32_t img_w, int32_t img_c,
+                          float min_box_size, float iou_thr, float score_thr, int32_t clip,
+                          float* out_boxes /*[cap,4]*/, float* out_scores /*[cap]*/, int32_t* out_labels /*[cap]*/,
+                          int64_t cap, int64_t* n_out);
+
 /* replaces: bbox_utils.compute_iou (bbox_utils.py:200-214 = inference_tiled.py:103-117).
  * iou[j] = IoU(box, boxes[j]) in the reference's fp32 operand order (0/0 -> NaN). */
 y3_status y3_compute_iou(y3_handle h, const float* box /*[4]*/, const float* boxes /*[m,4]*/,
@@ -188,12 +198,50 @@ y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dtype, y3_mem im
                          float min_box_size, float iou_thr, float score_thr,
                          double* preds, y3_mem preds_mem, int64_t cap, int64_t* n_out);
 
+/* Page-locked host memory for images (pinned-host staging).  An image that lives in such a buffer
+ * is uploaded by y3_infer_tiled band by band on a copy stream while the previous tile batch computes; a pageable image
+ * works too, but its copies are staged synchronously by the driver.  imagereader.imread reads into these buffers. */
+y3_status y3_host_alloc(int64_t bytes, void** out);
+void y3_host_free(void* p);
+
+/* Optional final stage of the tiled path that the reference does NOT have (it resolves seams by centre ownership only,
+ * inference_tiled.py:235-254) and BASELINE.json's north_star asks for: among the boxes of preds [n,6] (float64 rows
+ * x0,y0,x1,y1,score,label as returned by y3_infer_tiled, integer pixel corners) whose extent crosses a zone boundary of
+ * the tile grid, greedy per-class NMS (same IoU arithmetic and tie rule as y3_single_class_nms) runs and suppressed rows
+ * are dropped; all other rows and the row order are untouched.  nc = number of classes (labels are 0..nc-1). */
+y3_status y3_cross_seam_nms(y3_handle h, const double* preds, y3_mem preds_mem, int64_t n, int32_t nc,
+                            int64_t img_h, int64_t img_w, int32_t tile_h, int32_t tile_w, int32_t edge_range, float iou_thr,
+                            double* out, y3_mem out_mem, int64_t cap, int64_t* n_out);
+
+/* Multi-GPU (the reference is single-process): one process per GPU, one handle per process.
+ * y3_comm_unique_id fills a 128-byte NCCL unique id on ONE rank; the host program broadcasts it (any transport) and
+ * every rank calls y3_comm_init(h, rank, nranks, id) once.  NCCL is loaded at run time (libnccl.so.2). */
+#define Y3_COMM_ID_BYTES 128
+y3_status y3_comm_unique_id(uint8_t* id /*[Y3_COMM_ID_BYTES]*/);
+y3_status y3_comm_init(y3_handle h, int32_t rank, int32_t nranks, const uint8_t* id);
+int32_t y3_comm_size(y3_handle h);
+
+/* replaces: inference_tiled.inference_image_tiled (inference_tiled.py:185-310) with the tile grid sharded across the
+ * ranks of the communicator: every rank runs a contiguous row band of tiles (slice, normalise, network, decode, NMS,
+ * ownership filter - no data-path collective), then the surviving rows are exchanged with ncclAllGather (counts, then
+ * padded records) on the handle's stream and laid end to end in rank (= tile) order, i.e. every rank returns exactly
+ * what y3_infer_tiled returns on one GPU.  img is the whole image in host memory or on THIS rank's device; only the
+ * rows of the rank's band are uploaded.  cross_seam != 0 appends y3_cross_seam_nms over the gathered rows.  Collective:
+ * all ranks must call it with the same arguments; a capacity overflow is reported by every rank together. */
+y3_status y3_infer_tiled_sharded(y3_handle h, const void* img, y3_dtype dtype, y3_mem img_mem,
+                                 int64_t img_h, int64_t img_w, int32_t img_c,
+                                 int32_t tile_h, int32_t tile_w, int32_t edge_range,
+                                 float min_box_size, float iou_thr, float score_thr, int32_t cross_seam,
+                                 double* preds, y3_mem preds_mem, int64_t cap, int64_t* n_out);
+
 /* Measurement hooks (not part of the reference surface): device time in ms of the stages of the
  * last y3_detect / y3_infer_tiled / NMS call, measured with CUDA events on the handle's stream,
  * and the number of kernels this library launched since the handle was created.  ms_decode is the fused
  * decode + threshold + small-box filter + compaction kernel alone (it is also contained in ms_nms). */
 typedef struct {
     float ms_total, ms_h2d, ms_prep, ms_conv, ms_decode, ms_nms, ms_stitch, ms_d2h;
+    float ms_comm;                  /* sharded path: count + record all-gathers, concatenation, optional cross-seam stage */
+    float reserved_;
     int64_t kernels_launched;
     int64_t candidates, kept;
 } y3_timings;

@@ -5,6 +5,7 @@
 #include "net.cuh"
 #include "postproc.cuh"
 #include "tiles.cuh"
+#include "comm.cuh"
 
 #include <algorithm>
 #include <mutex>
@@ -108,10 +109,11 @@ CandSource dets_source(const float* dets_dev, int64_t n_per_img, int n_img, int 
 }
 
 // fused: the candidates are thresholded straight from the raw heads of the last forward
-CandSource heads_source(const Net* net, int n_img, bool filter, float min_box, float score_thr, int head_set = 0) {
+CandSource heads_source(const Net* net, int n_img, bool filter, float min_box, float score_thr, int head_set = 0, bool clip = false) {
     CandSource s;
     s.from_heads = true;
     s.dec = net->decode_args(n_img, head_set);
+    if (clip) { s.dec.clip_w = (float)net->W; s.dec.clip_h = (float)net->H; }
     s.rows_per_image = net->rows_per_image; s.n_images = n_img; s.nc = net->nc;
     s.filter_small = filter; s.min_size = min_box; s.score_thr = score_thr;
     return s;
@@ -174,6 +176,7 @@ void y3_destroy(y3_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm) { try { comm_destroy(h); } catch (...) {} }
     delete h->net;
     delete h->post;
     delete h->tiler;
@@ -267,6 +270,61 @@ y3_status y3_detect(y3_handle h, const float* in, y3_mem in_mem, int32_t batch, 
     total.stop();
     flush_phases(h);
     T.kernels_launched = h->kernels_launched;
+    Y3_API_END(h)
+}
+
+y3_status y3_detect_image(y3_handle h, const void* img, y3_dtype dt, y3_mem img_mem, int32_t H, int32_t W, int32_t C, float min_box,
+                          float iou_thr, float score_thr, int32_t clip, float* out_boxes, float* out_scores, int32_t* out_labels,
+                          int64_t cap, int64_t* n_out) {
+    Y3_API_BEGIN(h)
+    Net* net = net_of(h);
+    Tiler* T = tiler_of(h);
+    Y3_CHECK(img && n_out, Y3_ERR_INVALID, "NULL pointer");
+    Y3_CHECK(H == net->H && W == net->W && C == net->C, Y3_ERR_INVALID, "image %dx%dx%d does not match the network input %dx%dx%d",
+             H, W, C, net->H, net->W, net->C);
+    y3_timings& Tm = h->timings;
+    Tm = y3_timings{};
+    Phase total(h, &Tm.ms_total);
+    const size_t in_bytes = (size_t)H * W * C * dtype_size(dt);
+    const void* d_img;
+    { Phase p(h, &Tm.ms_h2d); d_img = to_device(h, img, img_mem, in_bytes, T->img); p.stop(); }
+    {   // whole-image z-score (imagereader.py:34-46) + HWC -> NCHW: the tile front-end with one tile = the image
+        Phase p(h, &Tm.ms_prep);
+        if (!T->geo1_ready || T->geo1_h != H || T->geo1_w != W) {
+            TileGeo g{};
+            g.y0 = 0; g.y1 = H; g.x0 = 0; g.x1 = W;
+            T->geo1.reserve(sizeof(TileGeo));
+            Y3_CUDA(cudaMemcpyAsync(T->geo1.p, &g, sizeof(TileGeo), cudaMemcpyHostToDevice, h->stream));
+            Y3_CUDA(cudaStreamSynchronize(h->stream));         // g is a host temporary
+            T->geo1_ready = true; T->geo1_h = H; T->geo1_w = W;
+        }
+        T->tiles.reserve((size_t)net->maxB * C * H * W * 4);
+        T->sums.reserve(16 * (size_t)net->maxB);
+        launch_tile_norm(h, d_img, dt, 0, W, C, T->geo1.as<TileGeo>(), 1, H, W, T->tiles.as<float>(), nullptr, T->sums.as<double>());
+        p.stop();
+    }
+    { Phase p(h, &Tm.ms_conv); net->forward(T->tiles.as<float>(), 1); p.stop(); }
+    NmsResult R;
+    {
+        Phase p(h, &Tm.ms_nms);
+        post_of(h)->enqueue(heads_source(net, 1, true, min_box, score_thr, 0, clip != 0), iou_thr);
+        p.stop();
+        R = post_of(h)->finish();
+    }
+    Tm.candidates = R.n_cand; Tm.kept = R.n_kept;
+    *n_out = R.n_kept;
+    Y3_CHECK(R.n_kept <= cap, Y3_ERR_NOSPACE, "output capacity %lld < %lld kept boxes", (long long)cap, (long long)R.n_kept);
+    if (R.n_kept) {
+        Phase p(h, &Tm.ms_d2h);
+        Y3_CHECK(out_boxes && out_scores && out_labels, Y3_ERR_INVALID, "NULL output");
+        Y3_CUDA(cudaMemcpyAsync(out_boxes, R.boxes, (size_t)R.n_kept * 16, cudaMemcpyDeviceToHost, h->stream));
+        Y3_CUDA(cudaMemcpyAsync(out_scores, R.scores, (size_t)R.n_kept * 4, cudaMemcpyDeviceToHost, h->stream));
+        Y3_CUDA(cudaMemcpyAsync(out_labels, R.labels, (size_t)R.n_kept * 4, cudaMemcpyDeviceToHost, h->stream));
+        p.stop();
+    }
+    total.stop();
+    flush_phases(h);
+    Tm.kernels_launched = h->kernels_launched;
     Y3_API_END(h)
 }
 
@@ -616,10 +674,11 @@ y3_status y3_stitch_tiles(y3_handle h, const float* dets, y3_mem dets_mem, int64
     Y3_API_END(h)
 }
 
-y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dt, y3_mem img_mem, int64_t H, int64_t W, int32_t C, int32_t th,
-                         int32_t tw, int32_t edge, int64_t tile_first, int64_t tile_count, float min_box, float iou_thr,
-                         float score_thr, double* preds, y3_mem preds_mem, int64_t cap, int64_t* n_out) {
-    Y3_API_BEGIN(h)
+namespace {
+// inference_image_tiled for tiles [tile_first, tile_first + tile_count): shared by y3_infer_tiled and the sharded entry
+void infer_tiled_impl(y3_handle h, const void* img, y3_dtype dt, y3_mem img_mem, int64_t H, int64_t W, int32_t C, int32_t th,
+                      int32_t tw, int32_t edge, int64_t tile_first, int64_t tile_count, float min_box, float iou_thr,
+                      float score_thr, double* preds, y3_mem preds_mem, int64_t cap, int64_t* n_out) {
     Net* net = net_of(h);
     Y3_CHECK(img && n_out, Y3_ERR_INVALID, "NULL pointer");
     Y3_CHECK(th == net->H && tw == net->W && C == net->C, Y3_ERR_INVALID,
@@ -631,7 +690,6 @@ y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dt, y3_mem img_m
     Y3_CHECK(tile_first >= 0 && tile_count >= 0 && tile_first + tile_count <= (int64_t)geo.size(), Y3_ERR_INVALID,
              "tile range [%lld,+%lld) outside 0..%zu", (long long)tile_first, (long long)tile_count, geo.size());
     y3_timings& Tm = h->timings;
-    Tm = y3_timings{};
     Phase total(h, &Tm.ms_total);
     T->acc_rows = 0;
     *n_out = 0;
@@ -731,10 +789,169 @@ y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dt, y3_mem img_m
           p.stop(); }
     }
     total.stop();
+}
+}  // namespace
+
+y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dt, y3_mem img_mem, int64_t H, int64_t W, int32_t C, int32_t th,
+                         int32_t tw, int32_t edge, int64_t tile_first, int64_t tile_count, float min_box, float iou_thr,
+                         float score_thr, double* preds, y3_mem preds_mem, int64_t cap, int64_t* n_out) {
+    Y3_API_BEGIN(h)
+    h->timings = y3_timings{};
+    infer_tiled_impl(h, img, dt, img_mem, H, W, C, th, tw, edge, tile_first, tile_count, min_box, iou_thr, score_thr, preds, preds_mem,
+                     cap, n_out);
     flush_phases(h);
     if (getenv("Y3_DEBUG_TIMING"))
-        fprintf(stderr, "y3: total %.2f ms, batch loop %.2f ms, stage sum %.2f ms\n", Tm.ms_total, T->dbg_loop,
-                Tm.ms_h2d + Tm.ms_prep + Tm.ms_conv + Tm.ms_nms + Tm.ms_stitch + Tm.ms_d2h);
+        fprintf(stderr, "y3: total %.2f ms, stage sum %.2f ms\n", h->timings.ms_total,
+                h->timings.ms_h2d + h->timings.ms_prep + h->timings.ms_conv + h->timings.ms_nms + h->timings.ms_stitch + h->timings.ms_d2h);
+    h->timings.kernels_launched = h->kernels_launched;
+    Y3_API_END(h)
+}
+
+y3_status y3_host_alloc(int64_t bytes, void** out) {
+    if (!out || bytes <= 0) { g_create_error = "y3_host_alloc: bad arguments"; return Y3_ERR_INVALID; }
+    *out = nullptr;
+    const cudaError_t e = cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        g_create_error = std::string("cudaHostAlloc failed: ") + cudaGetErrorString(e);
+        return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? Y3_ERR_NODEVICE : Y3_ERR_CUDA;
+    }
+    return Y3_OK;
+}
+
+void y3_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------------------------------- cross-seam stage
+y3_status y3_cross_seam_nms(y3_handle h, const double* preds, y3_mem preds_mem, int64_t n, int32_t nc, int64_t H, int64_t W,
+                            int32_t th, int32_t tw, int32_t edge, float iou_thr, double* out, y3_mem out_mem, int64_t cap, int64_t* n_out) {
+    Y3_API_BEGIN(h)
+    Y3_CHECK(n_out && n >= 0 && nc >= 1 && (n == 0 || preds), Y3_ERR_INVALID, "bad arguments");
+    *n_out = 0;
+    if (n > 0) {
+        Tiler* T = tiler_of(h);
+        const double* d = static_cast<const double*>(to_device(h, preds, preds_mem, (size_t)n * 48, T->dets));
+        const StitchArgs S{H, W, th, tw, edge};
+        const int64_t k = T->cross_seam(post_of(h), d, n, S, nc, iou_thr);
+        *n_out = k;
+        Y3_CHECK(k <= cap, Y3_ERR_NOSPACE, "output capacity %lld < %lld rows", (long long)cap, (long long)k);
+        if (k) {
+            Y3_CHECK(out, Y3_ERR_INVALID, "NULL output");
+            from_device(h, out, out_mem, T->seam_out.p, (size_t)k * 48);
+        }
+        Y3_CUDA(cudaStreamSynchronize(h->stream));
+        flush_phases(h);
+    }
+    Y3_API_END(h)
+}
+
+// ---------------------------------------------------------------------------------------- sharded path (NCCL)
+y3_status y3_comm_unique_id(uint8_t* id) {
+    if (!id) { g_create_error = "y3_comm_unique_id: NULL argument"; return Y3_ERR_INVALID; }
+    try {
+        comm_unique_id(id);
+        return Y3_OK;
+    } catch (const Error& e) {
+        g_create_error = e.msg;
+        return e.code;
+    }
+}
+
+y3_status y3_comm_init(y3_handle h, int32_t rank, int32_t nranks, const uint8_t* id) {
+    Y3_API_BEGIN(h)
+    Y3_CHECK(nranks == 1 || id, Y3_ERR_INVALID, "NULL unique id");
+    comm_init(h, rank, nranks, id);
+    Y3_API_END(h)
+}
+
+int32_t y3_comm_size(y3_handle h) { return h ? comm_size(h) : 0; }
+
+y3_status y3_infer_tiled_sharded(y3_handle h, const void* img, y3_dtype dt, y3_mem img_mem, int64_t H, int64_t W, int32_t C,
+                                 int32_t th, int32_t tw, int32_t edge, float min_box, float iou_thr, float score_thr,
+                                 int32_t cross_seam, double* preds, y3_mem preds_mem, int64_t cap, int64_t* n_out) {
+    Y3_API_BEGIN(h)
+    Y3_CHECK(n_out, Y3_ERR_INVALID, "NULL pointer");
+    Y3_CHECK(h->comm, Y3_ERR_STATE, "y3_comm_init has not been called on this handle");
+    Net* net = net_of(h);
+    Tiler* T = tiler_of(h);
+    const int rank = comm_rank(h), world = comm_size(h);
+    Y3_CHECK(world <= 64, Y3_ERR_UNSUPPORTED, "more than 64 ranks");
+    const int64_t n_tiles = (int64_t)plan_tiles(H, W, th, tw, edge, nullptr, nullptr).size();
+    const int64_t per = (n_tiles + world - 1) / world;                       // contiguous row-band shard of this rank
+    const int64_t first = std::min<int64_t>((int64_t)rank * per, n_tiles);
+    const int64_t count = std::min<int64_t>(per, n_tiles - first);
+    y3_timings& Tm = h->timings;
+    Tm = y3_timings{};
+    *n_out = 0;
+    // 1. local shard -> device buffer.  An overflow must not keep this rank out of the collectives: it is carried
+    //    through the count exchange and every rank reports Y3_ERR_NOSPACE together.
+    const int64_t cap_local = std::max<int64_t>(cap, 1);
+    T->shard_local.reserve((size_t)cap_local * 48);
+    int64_t n_local = 0;
+    bool local_overflow = false;
+    try {
+        infer_tiled_impl(h, img, dt, img_mem, H, W, C, th, tw, edge, first, count, min_box, iou_thr, score_thr,
+                         T->shard_local.as<double>(), Y3_MEM_DEVICE, cap_local, &n_local);
+    } catch (const Error& e) {
+        if (e.code != Y3_ERR_NOSPACE) throw;
+        local_overflow = true;
+        for (auto& r_ : h->phase_log) { h->event_pool.push_back(r_.a); h->event_pool.push_back(r_.b); }
+        h->phase_log.clear();
+    }
+    Phase comm_phase(h, &Tm.ms_comm);
+    // 2. counts of every rank (a negative count flags an overflow)
+    T->shard_counts.reserve((size_t)(world + 1) * 8);
+    h->pin_small.reserve(1024);
+    long long* h_counts = h->pin_small.as<long long>();
+    h_counts[64] = local_overflow ? -(long long)std::max<int64_t>(n_local, 1) : (long long)n_local;
+    long long* d_counts = T->shard_counts.as<long long>();
+    Y3_CUDA(cudaMemcpyAsync(d_counts + world, h_counts + 64, 8, cudaMemcpyHostToDevice, h->stream));
+    comm_all_gather_i64(h, d_counts + world, d_counts, 1);
+    Y3_CUDA(cudaMemcpyAsync(h_counts, d_counts, (size_t)world * 8, cudaMemcpyDeviceToHost, h->stream));
+    Y3_CUDA(cudaStreamSynchronize(h->stream));
+    long long total = 0, max_c = 0;
+    bool any_overflow = false;
+    for (int r = 0; r < world; ++r) {
+        const long long c = h_counts[r];
+        if (c < 0) any_overflow = true;
+        total += c < 0 ? -c : c;
+        max_c = std::max(max_c, c);
+    }
+    *n_out = total;
+    Y3_CHECK(!any_overflow && total <= cap, Y3_ERR_NOSPACE, "output capacity %lld < %lld boxes", (long long)cap, total);
+    if (total > 0) {
+        // 3. records: one padded all-gather sized by the largest rank, then the ranks' rows are laid end to end
+        //    (rank order = tile order, the reference's output order)
+        T->shard_gather.reserve((size_t)world * max_c * 48);
+        comm_all_gather_f64(h, T->shard_local.as<double>(), T->shard_gather.as<double>(), (size_t)max_c * 6);
+        const bool to_caller = (preds_mem == Y3_MEM_DEVICE && preds && !cross_seam);
+        if (!to_caller) T->acc.reserve((size_t)total * 48);
+        double* dst = to_caller ? preds : T->acc.as<double>();
+        long long off = 0;
+        for (int r = 0; r < world; ++r) {
+            if (h_counts[r] > 0)
+                Y3_CUDA(cudaMemcpyAsync(dst + off * 6, T->shard_gather.as<double>() + (size_t)r * max_c * 6, (size_t)h_counts[r] * 48,
+                                        cudaMemcpyDeviceToDevice, h->stream));
+            off += h_counts[r];
+        }
+        int64_t n_final = total;
+        const double* final_dev = dst;
+        // 4. optional cross-seam NMS over the gathered boxes - identical on every rank
+        if (cross_seam) {
+            const StitchArgs S{H, W, th, tw, edge};
+            n_final = T->cross_seam(post_of(h), dst, total, S, net->nc, iou_thr);
+            final_dev = T->seam_out.as<double>();
+            *n_out = n_final;
+        }
+        if (n_final > 0 && !to_caller) {
+            Y3_CHECK(preds, Y3_ERR_INVALID, "NULL output");
+            from_device(h, preds, preds_mem, final_dev, (size_t)n_final * 48);
+        }
+    }
+    comm_phase.stop();
+    Y3_CUDA(cudaStreamSynchronize(h->stream));
+    flush_phases(h);
     Tm.kernels_launched = h->kernels_launched;
     Y3_API_END(h)
 }

@@ -11,6 +11,7 @@ struct DecodeArgs {
     float stride_h[3], stride_w[3];
     float anchor_w[Y3_MAX_ANCHORS], anchor_h[Y3_MAX_ANCHORS];
     int na, nc, pitch, n_total, batch;
+    float clip_w, clip_h;     // > 0: corners clipped to [0, clip_w] x [0, clip_h] (inference.py:62-65, np.clip) - decode_box only
 };
 
 #ifdef __CUDACC__
@@ -52,7 +53,12 @@ __device__ __forceinline__ float4 decode_box(const DecodeArgs& D, const float* h
     const float cy = __fmul_rn(__fadd_rn(sigmoid_f(ty), (float)gi), D.stride_w[s]);
     const float hw = __fdiv_rn(__fmul_rn(expf(tw), D.anchor_w[a]), 2.0f);
     const float hh = __fdiv_rn(__fmul_rn(expf(th), D.anchor_h[a]), 2.0f);
-    return make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+    float4 b = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+    if (D.clip_w > 0.f) {                         // np.clip(v, 0, hi) = minimum(maximum(v, 0), hi), NaN propagates
+        b.x = np_min(np_max(b.x, 0.f), D.clip_w); b.z = np_min(np_max(b.z, 0.f), D.clip_w);
+        b.y = np_min(np_max(b.y, 0.f), D.clip_h); b.w = np_min(np_max(b.w, 0.f), D.clip_h);
+    }
+    return b;
 }
 #endif
 

@@ -94,6 +94,7 @@ struct y3_context {
     cudaStream_t copy_stream = nullptr;          // H2D of the image band, overlapped with compute
     cudaStream_t post_stream = nullptr;          // candidates / sort / NMS / stitch of batch k while conv of k+1 runs
     y3::PinnedBuf pin_small;
+    void* comm = nullptr;                        // y3::Comm (comm.cu): NCCL communicator of the sharded path
 };
 
 namespace y3 {

@@ -540,6 +540,10 @@ static bool dl_compact(const DLTensor& t) {
 
 void Net::load(int n, const char* const* names, DLManagedTensor* const* tensors_in) {
     cudaStream_t st = ctx->stream;
+    // captured forwards bake kernel parameters in (the fused stem kernel takes its weights by value): drop them
+    Y3_CUDA(cudaStreamSynchronize(st));
+    for (GraphEntry& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
     for (int i = 0; i < n; ++i) {
         Y3_CHECK(names[i] && tensors_in[i], Y3_ERR_INVALID, "weight %d is NULL", i);
         const std::string full(names[i]);
@@ -653,6 +657,39 @@ void Net::load(int n, const char* const* names, DLManagedTensor* const* tensors_
 void Net::forward(const float* in_dev, int b, int head_set) {
     Y3_CHECK(loaded, Y3_ERR_STATE, "weights not (completely) loaded - missing %s", missing.c_str());
     Y3_CHECK(b >= 1 && b <= maxB, Y3_ERR_INVALID, "batch %d outside 1..%d", b, maxB);
+    // Batch-1 latency path (inference.py: one image per call): ~77 kernel launches of a few microseconds each are
+    // bound by the launch rate, so small batches replay a captured graph (keyed by input buffer, batch and head set).
+    static const int graph_max = getenv("Y3_GRAPH_MAX_BATCH") ? atoi(getenv("Y3_GRAPH_MAX_BATCH")) : 4;
+    if (b > graph_max) { forward_eager(in_dev, b, head_set); return; }
+    for (const GraphEntry& g : graphs)
+        if (g.in == in_dev && g.b == b && g.head_set == head_set) {
+            Y3_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+            count_launch(ctx, g.launches);
+            return;
+        }
+    forward_eager(in_dev, b, head_set);                         // first call: eager (sets every function attribute, results valid)
+    if (graphs.size() >= 16) return;                            // callers with ever-changing buffers stay eager
+    const int64_t before = ctx->kernels_launched;
+    cudaGraph_t graph = nullptr;
+    Y3_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    try {
+        forward_eager(in_dev, b, head_set);
+    } catch (...) {
+        cudaStreamEndCapture(ctx->stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        throw;
+    }
+    Y3_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
+    GraphEntry g{in_dev, b, head_set, nullptr, (int)(ctx->kernels_launched - before)};
+    ctx->kernels_launched = before;                              // the capture launched nothing
+    const cudaError_t e = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    Y3_CHECK(e == cudaSuccess, Y3_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    graphs.push_back(g);
+}
+
+void Net::forward_eager(const float* in_dev, int b, int head_set) {
     for (size_t oi = 0; oi < ops.size(); ++oi) {
         Op& op = ops[oi];
         if (fuse_stem_conv1 && oi == 0) {
@@ -752,6 +789,7 @@ std::string Net::profile(int b, int iters) {
 }
 
 Net::~Net() {
+    for (GraphEntry& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (void* p : owned) cudaFree(p);
 }
 

@@ -74,6 +74,10 @@ struct Net {
     void build();
     void load(int n, const char* const* names, DLManagedTensor* const* tensors);
     void forward(const float* in_dev, int b, int head_set = 0);   // NCHW fp32 on the device -> heads[head_set]
+    void forward_eager(const float* in_dev, int b, int head_set);
+    // small batches replay a captured CUDA graph of the ~77 launches (the batch-1 forward is launch-bound)
+    struct GraphEntry { const float* in; int b, head_set; cudaGraphExec_t exec; int launches; };
+    std::vector<GraphEntry> graphs;
     void decode(int b);                         // heads -> boxes
     DecodeArgs decode_args(int b, int head_set = 0) const;   // for the fused decode+candidates path
     std::string profile(int b, int iters);      // per-layer CSV report

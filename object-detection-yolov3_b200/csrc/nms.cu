@@ -107,16 +107,15 @@ k_candidates(CandSource src, KeyLayout kl, int64_t total, float logit_floor, Can
                     s = __fsqrt_rn(__fmul_rn(p, o));
                     pass = (s >= thr);
                     if (pass && src.filter_small) {
-                        const float w = __fsub_rn(decode_corner(src.dec, hp, sc, cell, a, 2), decode_corner(src.dec, hp, sc, cell, a, 0));
-                        const float h = __fsub_rn(decode_corner(src.dec, hp, sc, cell, a, 3), decode_corner(src.dec, hp, sc, cell, a, 1));
-                        pass = (w > src.min_size) && (h > src.min_size);
+                        const float4 bx = decode_box(src.dec, hp, sc, cell, a);
+                        pass = (__fsub_rn(bx.z, bx.x) > src.min_size) && (__fsub_rn(bx.w, bx.y) > src.min_size);
                     }
                 }
             } else {
                 const float p = __ldg(src.cls + (int64_t)grow * src.cls_stride + c);
                 if (src.raw_scores) {
                     s = p;
-                    pass = true;
+                    pass = src.row_mask ? (src.row_mask[grow] != 0) : true;
                 } else {
                     const float o = src.obj ? __ldg(src.obj + (int64_t)grow * src.obj_stride) : 1.0f;
                     s = __fsqrt_rn(__fmul_rn(p, o));             // np.sqrt(class_probs * objectness)
@@ -129,8 +128,12 @@ k_candidates(CandSource src, KeyLayout kl, int64_t total, float logit_floor, Can
                     pass = (w > src.min_size) && (h > src.min_size);
                 }
             }
+            if (pass && src.row_seg) {
+                const int sg = src.row_seg[grow];
+                pass = sg >= 0 && sg < src.n_seg_override;       // a label outside the class range takes no part
+            }
             if (pass) {
-                seg = (uint32_t)((uint64_t)img * src.nc + (uint64_t)c);
+                seg = src.row_seg ? (uint32_t)src.row_seg[grow] : (uint32_t)((uint64_t)img * src.nc + (uint64_t)c);
                 key = make_key(kl, seg, s, (uint32_t)row);
                 val = (uint32_t)grow;
             }
@@ -173,9 +176,8 @@ k_candidates_heads1(CandSource src, KeyLayout kl, float logit_floor, CandOut O) 
                     s = __fsqrt_rn(__fmul_rn(sigmoid_f(lc), sigmoid_f(lo)));
                     pass = (s >= thr);
                     if (pass && src.filter_small) {
-                        const float w = __fsub_rn(decode_corner(src.dec, hp, sc, cell, a, 2), decode_corner(src.dec, hp, sc, cell, a, 0));
-                        const float h = __fsub_rn(decode_corner(src.dec, hp, sc, cell, a, 3), decode_corner(src.dec, hp, sc, cell, a, 1));
-                        pass = (w > src.min_size) && (h > src.min_size);
+                        const float4 bx = decode_box(src.dec, hp, sc, cell, a);
+                        pass = (__fsub_rn(bx.z, bx.x) > src.min_size) && (__fsub_rn(bx.w, bx.y) > src.min_size);
                     }
                 }
             }
@@ -252,9 +254,8 @@ k_candidates_rows(CandSource src, KeyLayout kl, float logit_floor, const uint32_
             }
             if (!any) continue;
             if (!size_known) {                                   // warp-uniform: every lane evaluates the same box
-                const float w = __fsub_rn(decode_corner(src.dec, hp, sc, cell, a, 2), decode_corner(src.dec, hp, sc, cell, a, 0));
-                const float h = __fsub_rn(decode_corner(src.dec, hp, sc, cell, a, 3), decode_corner(src.dec, hp, sc, cell, a, 1));
-                size_ok = (w > src.min_size) && (h > src.min_size);
+                const float4 bx = decode_box(src.dec, hp, sc, cell, a);
+                size_ok = (__fsub_rn(bx.z, bx.x) > src.min_size) && (__fsub_rn(bx.w, bx.y) > src.min_size);
                 size_known = true;
             }
             if (!size_ok) break;                                 // the whole row is dropped by filter_small_boxes
@@ -295,8 +296,7 @@ k_gather_sorted(CandSource src, const uint32_t* __restrict__ vals, int64_t n, fl
         const int64_t img = grow / src.rows_per_image;
         int sc, cell, a;
         const float* hp = head_row(src.dec, (int)img, (int)(grow - img * src.rows_per_image), &sc, &cell, &a);
-        bx = make_float4(decode_corner(src.dec, hp, sc, cell, a, 0), decode_corner(src.dec, hp, sc, cell, a, 1),
-                         decode_corner(src.dec, hp, sc, cell, a, 2), decode_corner(src.dec, hp, sc, cell, a, 3));
+        bx = decode_box(src.dec, hp, sc, cell, a);
     } else {
         const float* b = src.box + (int64_t)vals[p] * src.box_stride;
         bx = make_float4(__ldg(b), __ldg(b + 1), __ldg(b + 2), __ldg(b + 3));
@@ -702,7 +702,7 @@ int64_t PostProc::flag_offsets(const uint8_t* flags, int64_t n) {
 }
 
 KeyLayout PostProc::key_layout(const CandSource& src) const {
-    const int64_t nseg64 = (int64_t)src.n_images * src.nc;
+    const int64_t nseg64 = src.num_segments();
     KeyLayout kl;
     kl.row_bits = ilog2_ceil((uint64_t)src.rows_per_image);
     if (kl.row_bits == 0) kl.row_bits = 1;
@@ -789,7 +789,7 @@ void PostProc::enqueue(const CandSource& src, float iou_thr) {
     const KeyLayout kl = key_layout(src);
     const int64_t cap = capacity(src);
     static const bool no_seg = getenv("Y3_NMS_GLOBAL_SORT") != nullptr;      // A/B: the round-1 global-sort pipeline only
-    if (!no_seg && (int64_t)src.n_images * src.nc < (1ll << 24) && kl.seg_shift <= 62) {
+    if (!no_seg && src.num_segments() < (1ll << 24) && kl.seg_shift <= 62) {
         // segmented pipeline: bin by (image, class), per-segment NMS.  Segments are bounded by rows_per_image; when that
         // bound exceeds what one CTA sorts in shared memory the largest segment is read back before the route is chosen.
         segmented_front(src, kl, cap);
@@ -838,7 +838,7 @@ NmsResult PostProc::run_global_sort(const CandSource& src, float iou_thr, const 
     cudaStream_t st = ctx->stream;
     NmsResult R;
     R.n_cand = K;
-    const int nseg = (int)((int64_t)src.n_images * src.nc);
+    const int nseg = (int)src.num_segments();
     keys[1].reserve(cap * 8);
     vals[1].reserve(cap * 4);
     host_small.reserve(64 + (size_t)(nseg + 1) * 8);

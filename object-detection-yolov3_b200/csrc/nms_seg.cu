@@ -167,7 +167,7 @@ __device__ __forceinline__ void warp_select_nms(const SegArgs& A, const uint64_t
     float4 b[PL];
     float a[PL];
     unsigned alive = 0, odd = 0;                                 // odd: a non-finite coordinate / area -> exact IoU path
-    const int img = seg / A.src.nc;
+    const int img = A.src.seg_image(seg);
     const bool thr_plain = A.thr > 0.f && A.thr < 1e30f;
 #pragma unroll
     for (int k = 0; k < PL; ++k) {
@@ -319,7 +319,7 @@ k2_nms_cta(const SegArgs A, uint64_t* __restrict__ bkeys, const int* __restrict_
         const int seg = work_list[item];
         const int s0 = seg_off[seg];
         const int m = seg_off[seg + 1] - s0;
-        const int img = seg / A.src.nc;
+        const int img = A.src.seg_image(seg);
         // 1. sort the segment's keys
         for (int j = threadIdx.x; j < m; j += NMS_THREADS) s_keys[j] = bkeys[s0 + j];
         __syncthreads();
@@ -429,7 +429,7 @@ k2_emit(const SegArgs A, const int* __restrict__ seg_off, const int* __restrict_
         const int n = kept_cnt[seg];
         if (n <= 0) continue;
         const int s0 = seg_off[seg], q0 = out_off[seg];
-        const int img = seg / A.src.nc, label = seg - img * A.src.nc;
+        const int img = A.src.seg_image(seg), label = A.src.seg_label(seg);
         TileGeo g{};
         if (A.tiled) g = A.geo[img];
         for (int t = lane; t < n; t += 32) {
@@ -463,7 +463,7 @@ bool PostProc::segmented_ok(const CandSource& src) { return src.rows_per_image <
 
 static SegArgs seg_args(const CandSource& src, const KeyLayout& kl, float thr, const StitchCtx* st) {
     SegArgs A;
-    A.src = src; A.kl = kl; A.thr = thr; A.nseg = (int)((int64_t)src.n_images * src.nc);
+    A.src = src; A.kl = kl; A.thr = thr; A.nseg = (int)src.num_segments();
     A.tiled = st ? 1 : 0;
     A.geo = st ? st->geo : nullptr;
     A.S = st ? st->S : StitchArgs{};
@@ -479,7 +479,7 @@ static void ensure_ctrl(PostProc* P) {
 
 void PostProc::segmented_front(const CandSource& src, const KeyLayout& kl, int64_t cap) {
     cudaStream_t st = ctx->stream;
-    const int nseg = (int)((int64_t)src.n_images * src.nc);
+    const int nseg = (int)src.num_segments();
     Y3_CHECK(cap < (1ll << 31), Y3_ERR_UNSUPPORTED, "candidate capacity %lld too large", (long long)cap);
     ensure_ctrl(this);
     seg_cnt.reserve((size_t)(nseg + 1) * 4); seg_off32.reserve((size_t)(nseg + 1) * 4);
@@ -598,7 +598,7 @@ void PostProc::begin_tiled() {
 
 bool PostProc::run_tiled(const CandSource& src, float iou_thr, const StitchCtx& stc) {
     static const bool no_seg = getenv("Y3_NMS_GLOBAL_SORT") != nullptr;
-    if (no_seg || !segmented_ok(src) || (int64_t)src.n_images * src.nc >= (1ll << 24)) return false;
+    if (no_seg || !segmented_ok(src) || src.num_segments() >= (1ll << 24)) return false;
     const int64_t rows = src.rows_per_image * src.n_images;
     if (rows <= 0) return true;
     Y3_CHECK(rows < (1ll << 32), Y3_ERR_UNSUPPORTED, "too many rows (%lld)", (long long)rows);

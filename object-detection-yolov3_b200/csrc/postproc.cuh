@@ -57,6 +57,16 @@ struct CandSource {
     float score_thr = 0.1f;      // ignored when raw_scores
     bool from_heads = false;     // fused path: decode on the fly from the raw fp32 heads (no decoded tensor)
     DecodeArgs dec;              // valid when from_heads
+    // Rows that carry their own segment id (the cross-seam stage: one list of boxes with a label each).  Needs
+    // raw_scores, nc == 1, n_images == 1; row_mask (optional) selects the rows that take part at all.
+    const int32_t* row_seg = nullptr;
+    const uint8_t* row_mask = nullptr;
+    int32_t n_seg_override = 0;
+    int64_t num_segments() const { return row_seg ? (int64_t)n_seg_override : (int64_t)n_images * nc; }
+#ifdef __CUDACC__
+    __host__ __device__ int seg_image(int seg) const { return row_seg ? 0 : seg / nc; }
+    __host__ __device__ int seg_label(int seg) const { return row_seg ? seg : seg % nc; }
+#endif
 };
 
 // Result lives in PostProc-owned device buffers until the next run().

@@ -279,4 +279,72 @@ int64_t Tiler::stitch(PostProc* post, const NmsResult& R, const TileGeo* geo_dev
     return total;
 }
 
+// ------------------------------------------------------------------------------------------ cross-seam NMS
+// Seam candidates: rows whose inclusive pixel extent straddles a zone boundary (zone = tile - 2*edge on every axis that
+// is actually tiled, inference_tiled.py:41-47) - the boxes two neighbouring tiles can both have reported.
+__global__ void __launch_bounds__(256)
+k_seam_prepare(const double* __restrict__ preds, int64_t n, int zone_y, int zone_x, float4* __restrict__ box,
+               float* __restrict__ score, int32_t* __restrict__ label, uint8_t* __restrict__ cand, uint8_t* __restrict__ keepm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* p = preds + i * 6;
+    const double x0 = p[0], y0 = p[1], x1 = p[2], y1 = p[3];
+    bool c = false;
+    if (zone_y > 0) c |= floor(y0 / zone_y) != floor(y1 / zone_y);
+    if (zone_x > 0) c |= floor(x0 / zone_x) != floor(x1 / zone_x);
+    box[i] = make_float4((float)x0, (float)y0, (float)x1, (float)y1);
+    score[i] = (float)p[4];
+    label[i] = (int32_t)p[5];
+    cand[i] = c ? 1 : 0;
+    keepm[i] = c ? 0 : 1;                       // non-candidates always stay
+}
+__global__ void __launch_bounds__(256)
+k_seam_mark(const int32_t* __restrict__ src_row, int64_t n_kept, uint8_t* __restrict__ keepm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_kept) keepm[src_row[i]] = 1;
+}
+__global__ void __launch_bounds__(CMP_BLOCK)
+k_rows_scatter(const uint8_t* __restrict__ flags, int64_t n, const int* __restrict__ blk, const double* __restrict__ in,
+               double* __restrict__ out) {
+    __shared__ int s_w[CMP_BLOCK / 32];
+    const int64_t p = (int64_t)blockIdx.x * CMP_BLOCK + threadIdx.x;
+    const bool f = p < n && flags[p];
+    const int rank = block_rank(f, s_w);
+    if (f) {
+        const double* src = in + p * 6;
+        double* o = out + ((int64_t)blk[blockIdx.x] + rank) * 6;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) o[k] = src[k];
+    }
+}
+
+int64_t Tiler::cross_seam(PostProc* post, const double* preds_dev, int64_t n, const StitchArgs& S, int nc, float iou_thr) {
+    if (n <= 0) return 0;
+    cudaStream_t st = ctx->stream;
+    seam_box.reserve((size_t)n * 16); seam_score.reserve((size_t)n * 4); seam_label.reserve((size_t)n * 4);
+    seam_cand.reserve((size_t)n); seam_keep.reserve((size_t)n); seam_out.reserve((size_t)n * 48);
+    const int zone_y = S.tile_h >= S.img_h ? 0 : S.tile_h - 2 * S.edge;
+    const int zone_x = S.tile_w >= S.img_w ? 0 : S.tile_w - 2 * S.edge;
+    k_seam_prepare<<<ceil_div(n, 256), 256, 0, st>>>(preds_dev, n, zone_y, zone_x, seam_box.as<float4>(), seam_score.as<float>(),
+                                                     seam_label.as<int32_t>(), seam_cand.as<uint8_t>(), seam_keep.as<uint8_t>());
+    Y3_LAUNCHED(ctx);
+    CandSource src;
+    src.box = seam_box.as<float>(); src.box_stride = 4;
+    src.cls = seam_score.as<float>(); src.cls_stride = 1; src.obj = nullptr;
+    src.rows_per_image = n; src.n_images = 1; src.nc = 1; src.raw_scores = true;
+    src.row_seg = seam_label.as<int32_t>(); src.row_mask = seam_cand.as<uint8_t>(); src.n_seg_override = nc;
+    const NmsResult R = post->run(src, iou_thr);
+    if (R.n_kept > 0) {
+        k_seam_mark<<<ceil_div(R.n_kept, 256), 256, 0, st>>>(R.src_row, R.n_kept, seam_keep.as<uint8_t>());
+        Y3_LAUNCHED(ctx);
+    }
+    const int64_t total = post->flag_offsets(seam_keep.as<uint8_t>(), n);
+    if (total > 0) {
+        k_rows_scatter<<<ceil_div(n, CMP_BLOCK), CMP_BLOCK, 0, st>>>(seam_keep.as<uint8_t>(), n, post->blk.as<int>(), preds_dev,
+                                                                     seam_out.as<double>());
+        Y3_LAUNCHED(ctx);
+    }
+    return total;
+}
+
 }  // namespace y3

@@ -16,11 +16,20 @@ void launch_tile_raw(y3_context* ctx, const void* img_dev, int esize, long long 
 struct Tiler {
     y3_context* ctx;
     DevBuf geo, img, tiles, ibox, flags, acc, dets, sums;
+    DevBuf seam_box, seam_score, seam_label, seam_cand, seam_keep, seam_out;      // cross-seam stage
+    DevBuf shard_local, shard_gather, shard_counts;                               // sharded path (comm.cu)
+    DevBuf geo1;                                                                  // one "tile" = the whole image (y3_detect_image)
+    bool geo1_ready = false;
+    int geo1_h = 0, geo1_w = 0;
     int64_t acc_rows = 0;
     float dbg_loop = 0.f;
     explicit Tiler(y3_context* c) : ctx(c) {}
     // appends the surviving boxes of R (image index = tile index inside geo_dev) to acc; returns how many
     int64_t stitch(PostProc* post, const NmsResult& R, const TileGeo* geo_dev, const StitchArgs& S);
+    // Optional final stage (north_star; not in the reference): greedy per-class NMS among the boxes whose extent crosses
+    // a zone boundary of the tile grid; suppressed rows are dropped, order kept.  preds_dev [n,6] float64 on the device
+    // -> seam_out (device), returns the surviving row count.  Synchronises the stream.
+    int64_t cross_seam(PostProc* post, const double* preds_dev, int64_t n, const StitchArgs& S, int nc, float iou_thr);
 };
 
 }  // namespace y3

@@ -2,7 +2,9 @@
 The LMDB training reader is out of scope."""
 import numpy as np
 
-from yolo3_b200 import post_engine
+from yolo3_b200 import pinned_copy, post_engine
+
+PIN_MIN_BYTES = 32 << 20      # images at least this large are returned in page-locked memory (see imread)
 
 
 def zscore_normalize(image_data):
@@ -11,8 +13,7 @@ def zscore_normalize(image_data):
     return post_engine().zscore(np.asarray(image_data))
 
 
-def imread(fp):
-    """skimage.io.imread replacement (skimage is not a dependency): HxW or HxWxC array."""
+def _decode(fp):
     try:
         import cv2
         img = cv2.imread(fp, cv2.IMREAD_UNCHANGED)
@@ -24,6 +25,19 @@ def imread(fp):
         pass
     from PIL import Image
     return np.asarray(Image.open(fp))
+
+
+def imread(fp):
+    """skimage.io.imread replacement (skimage is not a dependency): HxW or HxWxC array.  Large images come back in
+    page-locked host memory (y3_host_alloc), so that inference_tiled uploads them band by band on a copy stream while
+    the previous tile batch computes - the staging the reference leaves to TensorFlow's feed path."""
+    img = _decode(fp)
+    if img.nbytes >= PIN_MIN_BYTES:
+        try:
+            return pinned_copy(np.ascontiguousarray(img))
+        except Exception:          # no CUDA device in this process: the decoded array is still a valid result
+            return img
+    return img
 
 
 def imwrite(img, fp):

@@ -36,6 +36,18 @@ def _detect_one(yolo_model, img, min_box_size):
     if img.ndim == 2:
         img = img[:, :, None]
     height, width = img.shape[0], img.shape[1]
+    engine = yolo_model.engine_for((height, width)) if hasattr(yolo_model, "engine_for") else getattr(yolo_model, "engine", None)
+    if engine is not None and engine.img_size is not None and tuple(engine.img_size) == tuple(img.shape):
+        # the whole per-image body as ONE library call (y3_detect_image): z-score, forward, decode, clip, filter, NMS
+        print('  img.shape={}'.format(img.shape))
+        kept, _, labels = engine.detect_image(np.ascontiguousarray(img), min_box_size)
+        if kept.shape[0] == 0:
+            return np.zeros((0, 5), np.int32)
+        xywh = kept.copy()
+        xywh[:, 2] -= xywh[:, 0]
+        xywh[:, 3] -= xywh[:, 1]
+        return np.concatenate((xywh, labels.reshape(-1, 1)), axis=-1).astype(np.int32)
+    # foreign model object: the reference's sequence of calls, each stage on the GPU
     norm = imagereader.zscore_normalize(img.astype(np.float32))
     print('  img.shape={}'.format(norm.shape))
     batch = np.ascontiguousarray(norm.transpose((2, 0, 1))[None], dtype=np.float32)

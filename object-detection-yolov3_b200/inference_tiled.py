@@ -55,9 +55,13 @@ def inference_image_tiled(yolo_model, img, tile_size, min_roi_size):
         engine = getattr(yolo_model, "engine", None)
     if engine is not None and tuple(tile_size) == tuple(engine.img_size[:2]):
         if _distributed():
-            pred = infer_tiled_distributed(engine, img, tile_size, min_roi_size, EDGE_EFFECT_RANGE).cpu().numpy()
+            # tile grid sharded over the ranks; rows all-gathered (and, if enabled, the cross-seam stage run) by the library
+            pred = infer_tiled_distributed(engine, img, tile_size, min_roi_size, EDGE_EFFECT_RANGE, cross_seam=CROSS_SEAM_NMS,
+                                           out_device=None)
         else:
             pred = engine.infer_tiled(img, tile_size, min_roi_size, EDGE_EFFECT_RANGE)
+            if CROSS_SEAM_NMS:
+                pred = engine.cross_seam_nms(pred, img.shape[:2], tile_size, EDGE_EFFECT_RANGE, CROSS_SEAM_IOU_THRESHOLD)
     else:
         # foreign model object: slice + normalise on the GPU, call the model per tile as the
         # reference does, stitch on the GPU
@@ -65,9 +69,9 @@ def inference_image_tiled(yolo_model, img, tile_size, min_roi_size):
         tiles = post.tiles_normalized(img, tile_size, EDGE_EFFECT_RANGE)
         dets = np.stack([np.asarray(yolo_model(t[None], training=False))[0] for t in tiles])
         pred = post.stitch_tiles(dets, img.shape[:2], tile_size, min_roi_size, EDGE_EFFECT_RANGE)
-    if CROSS_SEAM_NMS:
-        nms_engine = engine if engine is not None else post_engine()
-        pred = nms_engine.cross_seam_nms(pred, img.shape[:2], tile_size, EDGE_EFFECT_RANGE, CROSS_SEAM_IOU_THRESHOLD)
+        if CROSS_SEAM_NMS:
+            pred = post.cross_seam_nms(pred, img.shape[:2], tile_size, EDGE_EFFECT_RANGE, CROSS_SEAM_IOU_THRESHOLD,
+                                       number_classes=dets.shape[2] - 5)
     print('Found: {} rois'.format(pred.shape[0]))
     return pred
 

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libyolo3_b200.so")
 Y3_MAX_ANCHORS = 8
 MEM_HOST, MEM_DEVICE = 0, 1
 U8, U16, I32, F32 = 0, 1, 2, 3
-ABI_VERSION = 2            # include/yolo3_b200.h Y3_ABI_VERSION this binding was written against
+ABI_VERSION = 3            # include/yolo3_b200.h Y3_ABI_VERSION this binding was written against
 OK, ERR_INVALID, ERR_CUDA, ERR_NOSPACE, ERR_STATE, ERR_UNSUPPORTED, ERR_NODEVICE = 0, -1, -2, -3, -4, -5, -6
 
 
@@ -27,6 +27,7 @@ class Y3Config(ctypes.Structure):
 class Y3Timings(ctypes.Structure):
     _fields_ = [("ms_total", c_float), ("ms_h2d", c_float), ("ms_prep", c_float), ("ms_conv", c_float),
                 ("ms_decode", c_float), ("ms_nms", c_float), ("ms_stitch", c_float), ("ms_d2h", c_float),
+                ("ms_comm", c_float), ("reserved_", c_float),
                 ("kernels_launched", c_int64), ("candidates", c_int64), ("kept", c_int64)]
 
 
@@ -42,6 +43,8 @@ PROTOTYPES = {
     "y3_boxes_per_image": (c_int64, [c_void_p]),
     "y3_detect": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_float, c_float, c_void_p, c_void_p,
                             c_void_p, c_void_p, c_int64, POINTER(c_int64)]),
+    "y3_detect_image": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_float, c_float, c_int32,
+                                  c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_int64)]),
     "y3_compute_iou": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "y3_filter_small": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p, c_void_p, c_int64,
                                   POINTER(c_int64)]),
@@ -60,6 +63,16 @@ PROTOTYPES = {
     "y3_infer_tiled": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int64, c_int32, c_int32, c_int32,
                                  c_int32, c_int64, c_int64, c_float, c_float, c_float, c_void_p, c_int32, c_int64,
                                  POINTER(c_int64)]),
+    "y3_host_alloc": (c_int32, [c_int64, POINTER(c_void_p)]),
+    "y3_host_free": (None, [c_void_p]),
+    "y3_cross_seam_nms": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int64, c_int64, c_int32, c_int32, c_int32,
+                                    c_float, c_void_p, c_int32, c_int64, POINTER(c_int64)]),
+    "y3_comm_unique_id": (c_int32, [c_void_p]),
+    "y3_comm_init": (c_int32, [c_void_p, c_int32, c_int32, c_void_p]),
+    "y3_comm_size": (c_int32, [c_void_p]),
+    "y3_infer_tiled_sharded": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int64, c_int32, c_int32, c_int32,
+                                         c_int32, c_float, c_float, c_float, c_int32, c_void_p, c_int32, c_int64,
+                                         POINTER(c_int64)]),
     "y3_get_timings": (c_int32, [c_void_p, POINTER(Y3Timings)]),
     "y3_bench_forward": (c_int32, [c_void_p, c_int32, c_int32, POINTER(c_float)]),
     "y3_profile_layers": (c_int32, [c_void_p, c_int32, c_int32, c_char_p, c_int64]),

@@ -152,6 +152,27 @@ class Engine:
             k = n.value
             return ob[:k], os_[:k], ol[:k], oi[:k]
 
+    def detect_image(self, img, min_box_size=32, iou_threshold=0.3, score_threshold=0.1, clip=True, cap=None):
+        """inference.py:47-79 for one HWC image of the network's size in ONE library call: whole-image z-score, forward
+        (CUDA graph), decode, clip to the image, small-box filter, per-class NMS.  -> boxes [n,4] f32, scores, labels."""
+        H, W, C = (int(v) for v in img.shape)
+        img, dt = _image_arg(img)
+        p, mem = _ptr(img)
+        cap = int(cap) if cap else 1 << 14
+        while True:
+            ob = np.empty((cap, 4), np.float32)
+            os_ = np.empty(cap, np.float32)
+            ol = np.empty(cap, np.int32)
+            n = ctypes.c_int64()
+            st = self.lib.y3_detect_image(self.h, p, dt, mem, H, W, C, float(min_box_size), float(iou_threshold), float(score_threshold),
+                                          1 if clip else 0, ob.ctypes.data, os_.ctypes.data, ol.ctypes.data, cap, ctypes.byref(n))
+            if st == _lib.ERR_NOSPACE and n.value > cap:
+                cap = int(n.value)
+                continue
+            check(st, self.h)
+            k = n.value
+            return ob[:k], os_[:k], ol[:k]
+
     # ------------------------------------------------------------------ tiled
     def infer_tiled(self, img, tile_size, min_box_size=32, edge_range=96, iou_threshold=0.3, score_threshold=0.1,
                     tile_first=0, tile_count=-1, cap=None, out_device=None):
@@ -231,28 +252,80 @@ class Engine:
             return out[:n.value]
 
     # ------------------------------------------------------------------ post-processing
-    def cross_seam_nms(self, pred, img_hw, tile_size, edge_range=96, iou_threshold=0.3):
+    def cross_seam_nms(self, pred, img_hw, tile_size, edge_range=96, iou_threshold=0.3, number_classes=None):
         """Optional final stage (north_star; NOT in the reference, which resolves seams by centre ownership
         only, inference_tiled.py:235-254): boxes whose extent crosses a zone boundary of the tile grid are
-        candidates, greedy per-class NMS (y3_single_class_nms on the GPU) runs among them, suppressed rows
+        candidates, greedy per-class NMS runs among them ON THE DEVICE (y3_cross_seam_nms), suppressed rows
         are dropped, everything else and the row order are untouched.  pred: float64 [n,6] as returned by
-        infer_tiled -> float64 [n',6]."""
-        pred = np.asarray(pred, np.float64)
-        cand = seam_candidates(pred, img_hw, tile_size, edge_range)
-        if not cand.any():
+        infer_tiled (numpy, or a torch CUDA tensor) -> same kind, float64 [n',6]."""
+        is_np = isinstance(pred, np.ndarray) or not hasattr(pred, "data_ptr")
+        if is_np:
+            pred = np.ascontiguousarray(np.asarray(pred, np.float64).reshape(-1, 6))
+        n = int(pred.shape[0])
+        if n == 0:
             return pred
-        drop = np.zeros(pred.shape[0], bool)
-        rows = np.nonzero(cand)[0]
-        labels = pred[rows, 5]
-        for c in np.unique(labels):
-            r = rows[labels == c]
-            if r.size < 2:
+        nc = int(number_classes) if number_classes else (self.number_classes if self.img_size is not None else
+                                                         int(float(pred[:, 5].max())) + 1)
+        if is_np:
+            out = np.empty((n, 6), np.float64)
+            op, om = out.ctypes.data, MEM_HOST
+        else:
+            import torch
+            pred = pred.contiguous()
+            out = torch.empty((n, 6), dtype=torch.float64, device=pred.device)
+            op, om = out.data_ptr(), MEM_DEVICE
+        p, mem = _ptr(pred)
+        k = ctypes.c_int64()
+        check(self.lib.y3_cross_seam_nms(self.h, p, mem, n, nc, int(img_hw[0]), int(img_hw[1]), int(tile_size[0]), int(tile_size[1]),
+                                         int(edge_range), float(iou_threshold), op, om, n, ctypes.byref(k)), self.h)
+        return out[:k.value]
+
+    # ------------------------------------------------------------------ multi-GPU (NCCL inside the library)
+    def comm_init(self, group=None):
+        """Creates the library's NCCL communicator over the ranks of a torch.distributed group: rank 0 draws the
+        unique id (y3_comm_unique_id), torch.distributed only carries its 128 bytes to the other ranks."""
+        import torch
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (ctypes.c_uint8 * 128)()
+            check(self.lib.y3_comm_unique_id(buf))
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        if world > 1:
+            backend = dist.get_backend(group)
+            carrier = ident.cuda(self.device) if backend == "nccl" else ident
+            dist.broadcast(carrier, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            ident = carrier.cpu()
+        raw = (ctypes.c_uint8 * 128)(*ident.tolist())
+        check(self.lib.y3_comm_init(self.h, rank, world, raw), self.h)
+        self._comm_world = world
+
+    def infer_tiled_sharded(self, img, tile_size, min_box_size=32, edge_range=96, iou_threshold=0.3, score_threshold=0.1,
+                            cross_seam=False, cap=None, out_device=None):
+        """y3_infer_tiled_sharded: every rank of the communicator runs its row band of tiles, the rows are
+        all-gathered by the library (NCCL on the handle's stream) - every rank gets the single-GPU result."""
+        H, W, C = (int(v) for v in img.shape)
+        img, dt = _image_arg(img)
+        p, mem = _ptr(img)
+        cap = int(cap) if cap else getattr(self, "_tiled_cap", 1 << 16)
+        while True:
+            if out_device is None:
+                out = np.empty((cap, 6), np.float64)
+                op, om = out.ctypes.data, MEM_HOST
+            else:
+                import torch
+                out = torch.empty((cap, 6), dtype=torch.float64, device=out_device)
+                op, om = out.data_ptr(), MEM_DEVICE
+            n = ctypes.c_int64()
+            st = self.lib.y3_infer_tiled_sharded(self.h, p, dt, mem, H, W, C, int(tile_size[0]), int(tile_size[1]), int(edge_range),
+                                                 float(min_box_size), float(iou_threshold), float(score_threshold),
+                                                 1 if cross_seam else 0, op, om, cap, ctypes.byref(n))
+            if st == _lib.ERR_NOSPACE and n.value > cap:          # reported by every rank together: all of them retry
+                cap = self._tiled_cap = 2 * int(n.value)
                 continue
-            keep = self.single_class_nms(pred[r, 0:4].astype(np.float32), pred[r, 4].astype(np.float32), iou_threshold)
-            gone = np.ones(r.size, bool)
-            gone[np.asarray(keep, np.int64)] = False
-            drop[r[gone]] = True
-        return pred[~drop]
+            check(st, self.h)
+            return out[:n.value]
 
     def compute_iou(self, box, boxes):
         box = np.ascontiguousarray(box, dtype=np.float32)
@@ -362,6 +435,43 @@ def tile_plan(img_h, img_w, tile_size, edge_range):
     return xs, ys
 
 
+class _PinnedBlock:
+    """One y3_host_alloc block, exposed through the array interface: numpy arrays made from it keep it alive
+    (arr.base), and it is returned to CUDA when the last of them goes away."""
+
+    def __init__(self, nbytes):
+        self.lib = _lib.load()
+        p = ctypes.c_void_p()
+        check(self.lib.y3_host_alloc(int(nbytes), ctypes.byref(p)))
+        self.ptr, self.nbytes = p.value, int(nbytes)
+        self.__array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.y3_host_free(ctypes.c_void_p(self.ptr))
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """numpy array in page-locked host memory (y3_host_alloc): images held in it are uploaded by y3_infer_tiled on a copy
+    stream, overlapped with compute.  Raises when the library has no CUDA device (no fallback)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape, dtype=np.int64))
+    block = _PinnedBlock(max(1, n * dtype.itemsize))
+    return np.asarray(block)[:n * dtype.itemsize].view(dtype).reshape(shape)
+
+
+def pinned_copy(a):
+    """copy of a numpy array in page-locked host memory"""
+    a = np.asarray(a)
+    out = pinned_empty(a.shape, a.dtype)
+    np.copyto(out, a)
+    return out
+
+
 _post = {}
 
 
@@ -399,18 +509,16 @@ def gather_rows(local, group=None):
 
 
 def infer_tiled_distributed(eng, img, tile_size, min_box_size=32, edge_range=96, iou_threshold=0.3,
-                            score_threshold=0.1, group=None):
-    """inference_image_tiled with the tile grid sharded across the ranks of a torch.distributed
-    (NCCL) group: every rank runs its row band of tiles on its own GPU (slice, normalise, conv stack,
-    decode, NMS, ownership filter - no data-path collective), then the surviving boxes are
-    all-gathered over NVLink and concatenated in rank (= tile) order.  -> torch float64 [n,6] (CUDA)."""
+                            score_threshold=0.1, group=None, cross_seam=False, out_device="auto"):
+    """inference_image_tiled with the tile grid sharded across the ranks of a torch.distributed group: every rank
+    runs its row band of tiles on its own GPU (slice, normalise, conv stack, decode, NMS, ownership filter - no
+    data-path collective), then the surviving boxes are all-gathered over NVLink BY THE LIBRARY (ncclAllGather on
+    the handle's stream, y3_infer_tiled_sharded) and laid end to end in rank (= tile) order; cross_seam appends
+    the cross-seam NMS stage on the device.  torch.distributed is used once, to hand the NCCL unique id around.
+    -> float64 [n,6]: a torch CUDA tensor (out_device "auto" / a device) or numpy (out_device None)."""
     import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    n_tiles = tile_count(img.shape[0], img.shape[1], tile_size, edge_range)
-    first, count = shard_range(n_tiles, rank, world)
-    dev = torch.device("cuda", eng.device)
-    local = eng.infer_tiled(img, tile_size, min_box_size, edge_range, iou_threshold, score_threshold,
-                            tile_first=first, tile_count=count, out_device=dev)
-    return gather_rows(local, group)
+    if getattr(eng, "_comm_world", None) is None:
+        eng.comm_init(group)
+    dev = torch.device("cuda", eng.device) if out_device == "auto" else out_device
+    return eng.infer_tiled_sharded(img, tile_size, min_box_size, edge_range, iou_threshold, score_threshold,
+                                   cross_seam=cross_seam, out_device=dev)

@@ -22,7 +22,7 @@ def test_header_symbols_exported():
     for s in syms:
         assert hasattr(lib, s), "missing export %s" % s
     assert sorted(_lib.PROTOTYPES) == syms, "ctypes prototypes out of sync with the header"
-    assert lib.y3_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.y3_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_tile_plan_host_logic(golden):

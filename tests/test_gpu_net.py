@@ -203,3 +203,48 @@ def test_forward_is_deterministic_at_bench_batch():
     # the same images in a smaller batch give the same heads (tile -> CTA assignment must not matter)
     part = eng.forward_heads(x[:5])
     assert all(np.array_equal(a[:5], b) for a, b in zip(first, part))
+
+
+def test_detect_image_is_the_reference_flow_in_one_call():
+    """y3_detect_image (inference.py:47-79 in one library call, CUDA-graph forward): whole-image z-score, forward, decode,
+    clip to the image, small-box filter, per-class NMS == the same stages run one by one (oracle z-score, the GPU's own
+    decoded boxes, then the reference-pinned NumPy / C post-processing) - bit-exact, twice (eager first call, graph replay)."""
+    from oracle import tiling_np as tl
+    img = (np.random.default_rng(9).integers(0, 4000, (416, 416, 3))).astype(np.uint16)
+    xn = tl.zscore(img.astype(np.float32)).transpose(2, 0, 1)[None]
+    x1 = torch.from_numpy(np.ascontiguousarray(xn))
+    eng, _ = calibrated((416, 416, 3), 4, None, 0.25, -3.0, x1, 2)
+    # the GPU's own z-score of the image (one tile = the whole image; within 2e-6 of the oracle's fp32 z-score, which is
+    # pinned separately in test_gpu_tiles) so that the stages after it can be compared bit for bit
+    xg = eng.tiles_normalized(img, (416, 416), 96, 0, 1)
+    np.testing.assert_allclose(xg, xn, rtol=0, atol=1e-5)
+    dec = eng.forward_boxes(xg)[0].copy()
+    for col, hi in ((0, 416), (1, 416), (2, 416), (3, 416)):
+        dec[:, col] = np.clip(dec[:, col], 0, hi)
+    d = pp.drop_small(dec, 32)
+    rb, rs, rl = nms_c.class_wise_nms(d[:, :4], d[:, 4:5], d[:, 5:], 0.3, 0.1)
+    assert len(rb) > 100 and (rb.min() == 0 or rb.max() == 416)          # the clip really acts on this input
+    for _ in range(3):
+        b, s, l = eng.detect_image(img, 32, 0.3, 0.1)
+        assert np.array_equal(b, rb) and np.array_equal(s, rs) and np.array_equal(l, rl)
+    # without the clip: the plain detect() of the normalised image
+    b0, s0, l0, _ = eng.detect(xg, 32, 0.3, 0.1)
+    b1, s1, l1 = eng.detect_image(img, 32, 0.3, 0.1, clip=False)
+    assert np.array_equal(b0, b1) and np.array_equal(s0, s1) and np.array_equal(l0, l1)
+
+
+def test_graph_replay_equals_eager_forward():
+    """small batches replay a captured CUDA graph of the forward: same heads as the eager launches, also after a weight reload"""
+    eng, ora = make((256, 256, 1), 1, max_batch=8)
+    x = np.random.default_rng(3).standard_normal((8, 1, 256, 256)).astype(np.float32)
+    big = eng.forward_heads(x)                      # batch 8: eager
+    for b in (1, 2, 3):
+        first = [h.copy() for h in eng.forward_heads(x[:b])]            # eager + capture
+        again = eng.forward_heads(x[:b])                                 # replay
+        assert all(np.array_equal(p, q) for p, q in zip(first, again))
+        assert all(np.array_equal(p, q[:b]) for p, q in zip(first, big))
+    W2 = mt.init_weights(1, 1, 3, seed=5, randomize_bn=True)
+    eng.load_weights({k: v.numpy() for k, v in W2.items()})
+    got = eng.forward_heads(x[:1])
+    want = mt.OracleNet(W2, (256, 256, 1), 1).feature_maps(torch.from_numpy(x[:1]))
+    assert max(mt.heads_rel_err(a, b.numpy()) for a, b in zip(got, want)) <= HEAD_TOL

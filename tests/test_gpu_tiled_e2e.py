@@ -75,3 +75,84 @@ def test_cross_seam_nms_matches_oracle():
     assert got.shape[0] < n and np.array_equal(got, want)
     # rows that do not straddle a seam are never touched
     assert np.array_equal(got[~seam_candidates(got, (H, W), tile, edge)], pred[~cand])
+
+
+def test_cross_seam_on_device_tensor():
+    """the cross-seam stage also takes rows that already live on the device (the sharded path feeds it that way)"""
+    import torch
+    from yolo3_b200 import post_engine
+    rng = np.random.default_rng(4)
+    H, W, tile, edge = 900, 1300, (256, 256), 32
+    n = 3000
+    cx, cy = rng.uniform(0, W, n), rng.uniform(0, H, n)
+    w, h = rng.uniform(10, 90, n), rng.uniform(10, 90, n)
+    pred = np.stack([np.clip(np.round(cx - w / 2), 0, W - 1), np.clip(np.round(cy - h / 2), 0, H - 1),
+                     np.clip(np.round(cx + w / 2), 0, W - 1), np.clip(np.round(cy + h / 2), 0, H - 1),
+                     pp.make_tie_free_scores(n, rng).astype(np.float64), rng.integers(0, 2, n).astype(np.float64)], axis=1)
+    want = tl.cross_seam_nms(pred, (H, W), tile, edge, 0.3)
+    got = post_engine().cross_seam_nms(torch.from_numpy(pred).cuda(), (H, W), tile, edge, 0.3, number_classes=2)
+    assert got.is_cuda and want.shape[0] < n and np.array_equal(got.cpu().numpy(), want)
+
+
+def test_sharded_entry_with_one_rank_equals_infer_tiled():
+    """y3_infer_tiled_sharded on a one-rank communicator (no NCCL traffic, same code path: shard -> counts -> records ->
+    concatenation -> optional cross-seam stage) returns y3_infer_tiled's rows; with the stage, the oracle's stage output"""
+    import ctypes
+    from yolo3_b200._lib import check
+    img = cases.synthetic_image(700, 900, 1, np.uint16, seed=700, blobs=20)
+    eng = standardised_engine(img, 64, 4)
+    want = eng.infer_tiled(img, TILE, 24, edge_range=64)
+    check(eng.lib.y3_comm_init(eng.h, 0, 1, None), eng.h)
+    assert eng.lib.y3_comm_size(eng.h) == 1
+    got = eng.infer_tiled_sharded(img, TILE, 24, edge_range=64)
+    assert want.shape[0] > 10 and np.array_equal(got, want)
+    seam = eng.infer_tiled_sharded(img, TILE, 24, edge_range=64, cross_seam=True)
+    assert np.array_equal(seam, tl.cross_seam_nms(want, img.shape[:2], TILE, 64, 0.3))
+    # capacity overflow is reported with the required row count and the call can be repeated
+    small = eng.infer_tiled_sharded(img, TILE, 24, edge_range=64, cap=3)
+    assert np.array_equal(small, want)
+
+
+def test_bench_workload_parity_2048_crop():
+    """the bench configuration itself - 512x512 tiles of a 1-channel uint16 image, EDGE_EFFECT_RANGE 96,
+    a 2048 x 2048 crop = 49 tiles, tile batch 32 (fused stem + conv2d_1 kernel, 2-CTA kernels, fp16 tail, segmented NMS with the
+    stitching folded in, software-pipelined post-processing over two batches).  y3_infer_tiled == the reference-pinned
+    oracle pipeline on the GPU's own decoded boxes, bit for bit; and against the fp32 oracle NETWORK on sampled tiles the
+    heads stay within 2e-2."""
+    import torch
+    from oracle import model_torch as mt
+    from yolo3_b200 import Engine, weights, tile_count
+    tile, edge, nc = (512, 512), 96, 1
+    anchors = [(32, 32), (128, 128), (256, 256)]
+    img = cases.synthetic_image(2048, 2048, 1, np.uint16, seed=7, blobs=60)
+    assert tile_count(2048, 2048, tile, edge) == 49
+    w = weights.random_init(1, nc, 3, seed=0, randomize_bn=True)
+    eng = Engine(tile + (1,), nc, anchors, max_batch=32)
+    eng.load_weights(w)
+    sample = eng.tiles_normalized(img, tile, edge, 0, 4)
+    E = 5 + nc
+    upd = {}
+    for i, h in enumerate(eng.forward_heads(sample)):
+        k = "feature_map_%d" % (i + 1)
+        mu, sd = h.mean(axis=(0, 2, 3)), np.maximum(h.std(axis=(0, 2, 3)), 1e-12)
+        want = np.zeros(3 * E)
+        want.reshape(3, E)[:, 4] = -3.0
+        upd[k + "/kernel"] = (w[k + "/kernel"] / sd[None, None, None, :]).astype(np.float32)
+        upd[k + "/bias"] = (want - mu / sd).astype(np.float32)
+    eng.load_weights(upd)
+    w.update(upd)
+    pred = eng.infer_tiled(img, tile, 32, edge_range=edge)
+    tiles = eng.tiles_normalized(img, tile, edge)
+    dets = np.concatenate([eng.forward_boxes(tiles[i:i + 32]) for i in range(0, len(tiles), 32)])
+    it = iter(range(len(tiles)))
+    want = tl.tiled_inference(lambda x: dets[next(it)][None], img, tile, 32, edge_range=edge, nms_fn=nms_c.greedy_nms)
+    print("boxes", pred.shape, want.shape)
+    assert want.shape[0] > 200 and np.array_equal(pred, want)
+    # network parity on sampled tiles (corner, edge, interior) against the fp32 oracle
+    ora = mt.OracleNet({k: torch.from_numpy(np.asarray(v)) for k, v in w.items()}, tile + (1,), nc, anchors)
+    idx = [0, 3, 24, 48]
+    got = eng.forward_heads(tiles[idx])
+    ref = ora.feature_maps(torch.from_numpy(tiles[idx]))
+    errs = [mt.heads_rel_err(a, b.numpy()) for a, b in zip(got, ref)]
+    print("head errors on sampled tiles", errs)
+    assert max(errs) <= 2e-2, errs
