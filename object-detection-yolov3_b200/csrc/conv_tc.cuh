@@ -51,9 +51,14 @@ void launch_conv(y3_context* ctx, const ConvLaunch& L);
 // predecessor in the stream drains; every thread executes griddepcontrol.wait before it touches activations.
 // Measured on B200 (round 1): no gain for this stack (12.88 vs 12.83 ms per 128 tiles) - the persistent CTAs hold
 // every SM until they exit, so there is nothing to overlap - hence off by default.
+// Small batches (the captured batch-1 forward) turn it on per call: there a kernel is a handful of tiles, most SMs are
+// free, and overlapping the next kernel's prologue (barrier init, TMEM allocation, tensor-map prefetch) with the tail
+// of the current one is worth ~6 % of the K1 forward (1.33 -> 1.25 ms).
+inline bool& pdl_for_small_batches() { static thread_local bool on = false; return on; }
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
-    static const bool pdl = getenv("Y3_PDL") != nullptr;
+    static const bool pdl_env = getenv("Y3_PDL") != nullptr;
+    const bool pdl = pdl_env || pdl_for_small_batches();
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];

@@ -661,6 +661,10 @@ void Net::forward(const float* in_dev, int b, int head_set) {
     // bound by the launch rate, so small batches replay a captured graph (keyed by input buffer, batch and head set).
     static const int graph_max = getenv("Y3_GRAPH_MAX_BATCH") ? atoi(getenv("Y3_GRAPH_MAX_BATCH")) : 4;
     if (b > graph_max) { forward_eager(in_dev, b, head_set); return; }
+    struct PdlScope {
+        PdlScope() { pdl_for_small_batches() = getenv("Y3_NO_PDL_SMALL") == nullptr; }
+        ~PdlScope() { pdl_for_small_batches() = false; }
+    } pdl_scope;
     for (const GraphEntry& g : graphs)
         if (g.in == in_dev && g.b == b && g.head_set == head_set) {
             Y3_CUDA(cudaGraphLaunch(g.exec, ctx->stream));

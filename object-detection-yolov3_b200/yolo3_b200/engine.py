@@ -135,7 +135,7 @@ class Engine:
         """forward -> filter_small_boxes -> per_class_nms on the device.  -> boxes, scores, labels, img_index."""
         batch = np.ascontiguousarray(batch, dtype=np.float32) if isinstance(batch, np.ndarray) else batch
         B = batch.shape[0]
-        cap = int(cap) if cap else 1 << 16
+        cap = int(cap) if cap else getattr(self, "_detect_cap", 1 << 16)
         p, mem = _ptr(batch)
         while True:
             ob = np.empty((cap, 4), np.float32)
@@ -146,7 +146,7 @@ class Engine:
             st = self.lib.y3_detect(self.h, p, mem, B, float(min_box_size), float(iou_threshold), float(score_threshold),
                                     ob.ctypes.data, os_.ctypes.data, ol.ctypes.data, oi.ctypes.data, cap, ctypes.byref(n))
             if st == _lib.ERR_NOSPACE and n.value > cap:
-                cap = int(n.value)
+                cap = self._detect_cap = 2 * int(n.value)      # sticky: later calls do not run twice
                 continue
             check(st, self.h)
             k = n.value
