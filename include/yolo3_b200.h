@@ -264,16 +264,6 @@ y3_status y3_profile_layers(y3_handle h, int32_t batch, int32_t iters, char* buf
 y3_status y3_debug_layer_output(y3_handle h, const char* layer, int32_t batch, float* out, int64_t cap_floats,
                                 int32_t* dims /*[3]*/);
 
-/* Hardware probe (test hook): UMMA K-major SWIZZLE_128B descriptors with row-shifted start addresses.
- * a_bf16 [512][64] bf16 bits; out [2][n_shift][128][64] fp32: variant 0 = base_offset 0, variant 1 =
- * base_offset (addr >> 7) & 7; entry (v, i) should equal rows shifts[i] .. shifts[i]+127 of a. */
-y3_status y3_debug_umma_rowshift(y3_handle h, const uint16_t* a_bf16, const int32_t* shifts, int32_t n_shift, float* out);
-
-/* Hardware probe (test hook): im2col-mode TMA loads of 128 output pixels x 64 channels.  x_bf16 NHWC bf16 bits;
- * probes [n][6] = c, w, h, n, tap_w, tap_h; out [n][128][64] = the raw (128B-swizzled) shared-memory tiles. */
-y3_status y3_debug_im2col(y3_handle h, const uint16_t* x_bf16, int32_t N, int32_t H, int32_t W, int32_t C, int32_t stride,
-                          int32_t pad_lo, int32_t pad_hi, int32_t ksize, const int32_t* probes, int32_t n_probe, uint16_t* out);
-
 #ifdef __cplusplus
 }
 #endif

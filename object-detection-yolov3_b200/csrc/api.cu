@@ -243,14 +243,14 @@ y3_status y3_detect(y3_handle h, const float* in, y3_mem in_mem, int32_t batch, 
     Y3_CHECK(batch >= 1 && batch <= net->maxB, Y3_ERR_INVALID, "batch %d outside 1..%d", batch, net->maxB);
     y3_timings& T = h->timings;
     T = y3_timings{};
-    Phase total(h, &T.ms_total);
+    Phase total(h, &T.ms_total, "y3:total");
     const size_t in_bytes = (size_t)batch * net->C * net->H * net->W * 4;
     const float* d_in;
-    { Phase p(h, &T.ms_h2d); d_in = static_cast<const float*>(to_device(h, in, in_mem, in_bytes, h->stage_in)); p.stop(); }
-    { Phase p(h, &T.ms_conv); net->forward(d_in, batch); p.stop(); }
+    { Phase p(h, &T.ms_h2d, "y3:h2d"); d_in = static_cast<const float*>(to_device(h, in, in_mem, in_bytes, h->stage_in)); p.stop(); }
+    { Phase p(h, &T.ms_conv, "y3:conv_stack"); net->forward(d_in, batch); p.stop(); }
     NmsResult R;
     {   // decode + score + threshold + small-box filter + compaction fused in one pass over the heads
-        Phase p(h, &T.ms_nms);
+        Phase p(h, &T.ms_nms, "y3:decode_nms_stitch");
         post_of(h)->enqueue(heads_source(net, batch, true, min_box, score_thr), iou_thr);
         p.stop();                                    // (ms_decode: the fused decode+threshold+compaction kernel alone)
         R = post_of(h)->finish();
@@ -259,7 +259,7 @@ y3_status y3_detect(y3_handle h, const float* in, y3_mem in_mem, int32_t batch, 
     *n_out = R.n_kept;
     Y3_CHECK(R.n_kept <= cap, Y3_ERR_NOSPACE, "output capacity %lld < %lld kept boxes", (long long)cap, (long long)R.n_kept);
     if (R.n_kept) {
-        Phase p(h, &T.ms_d2h);
+        Phase p(h, &T.ms_d2h, "y3:d2h");
         Y3_CHECK(out_boxes && out_scores && out_labels && out_img, Y3_ERR_INVALID, "NULL output");
         Y3_CUDA(cudaMemcpyAsync(out_boxes, R.boxes, (size_t)R.n_kept * 16, cudaMemcpyDeviceToHost, h->stream));
         Y3_CUDA(cudaMemcpyAsync(out_scores, R.scores, (size_t)R.n_kept * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -284,12 +284,12 @@ y3_status y3_detect_image(y3_handle h, const void* img, y3_dtype dt, y3_mem img_
              H, W, C, net->H, net->W, net->C);
     y3_timings& Tm = h->timings;
     Tm = y3_timings{};
-    Phase total(h, &Tm.ms_total);
+    Phase total(h, &Tm.ms_total, "y3:total");
     const size_t in_bytes = (size_t)H * W * C * dtype_size(dt);
     const void* d_img;
-    { Phase p(h, &Tm.ms_h2d); d_img = to_device(h, img, img_mem, in_bytes, T->img); p.stop(); }
+    { Phase p(h, &Tm.ms_h2d, "y3:h2d"); d_img = to_device(h, img, img_mem, in_bytes, T->img); p.stop(); }
     {   // whole-image z-score (imagereader.py:34-46) + HWC -> NCHW: the tile front-end with one tile = the image
-        Phase p(h, &Tm.ms_prep);
+        Phase p(h, &Tm.ms_prep, "y3:tile_slice_zscore");
         if (!T->geo1_ready || T->geo1_h != H || T->geo1_w != W) {
             TileGeo g{};
             g.y0 = 0; g.y1 = H; g.x0 = 0; g.x1 = W;
@@ -303,10 +303,10 @@ y3_status y3_detect_image(y3_handle h, const void* img, y3_dtype dt, y3_mem img_
         launch_tile_norm(h, d_img, dt, 0, W, C, T->geo1.as<TileGeo>(), 1, H, W, T->tiles.as<float>(), nullptr, T->sums.as<double>());
         p.stop();
     }
-    { Phase p(h, &Tm.ms_conv); net->forward(T->tiles.as<float>(), 1); p.stop(); }
+    { Phase p(h, &Tm.ms_conv, "y3:conv_stack"); net->forward(T->tiles.as<float>(), 1); p.stop(); }
     NmsResult R;
     {
-        Phase p(h, &Tm.ms_nms);
+        Phase p(h, &Tm.ms_nms, "y3:decode_nms_stitch");
         post_of(h)->enqueue(heads_source(net, 1, true, min_box, score_thr, 0, clip != 0), iou_thr);
         p.stop();
         R = post_of(h)->finish();
@@ -315,7 +315,7 @@ y3_status y3_detect_image(y3_handle h, const void* img, y3_dtype dt, y3_mem img_
     *n_out = R.n_kept;
     Y3_CHECK(R.n_kept <= cap, Y3_ERR_NOSPACE, "output capacity %lld < %lld kept boxes", (long long)cap, (long long)R.n_kept);
     if (R.n_kept) {
-        Phase p(h, &Tm.ms_d2h);
+        Phase p(h, &Tm.ms_d2h, "y3:d2h");
         Y3_CHECK(out_boxes && out_scores && out_labels, Y3_ERR_INVALID, "NULL output");
         Y3_CUDA(cudaMemcpyAsync(out_boxes, R.boxes, (size_t)R.n_kept * 16, cudaMemcpyDeviceToHost, h->stream));
         Y3_CUDA(cudaMemcpyAsync(out_scores, R.scores, (size_t)R.n_kept * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -380,11 +380,11 @@ y3_status y3_single_class_nms(y3_handle h, const float* boxes, const float* scor
     if (m > 0) {
         y3_timings& T = h->timings;
         T = y3_timings{};
-        Phase total(h, &T.ms_total);
+        Phase total(h, &T.ms_total, "y3:total");
         h->stage_in.reserve((size_t)m * 20);
         float* d_box = h->stage_in.as<float>();
         float* d_sc = d_box + 4 * m;
-        { Phase p(h, &T.ms_h2d);
+        { Phase p(h, &T.ms_h2d, "y3:h2d");
           Y3_CUDA(cudaMemcpyAsync(d_box, boxes, (size_t)m * 16, cudaMemcpyHostToDevice, h->stream));
           Y3_CUDA(cudaMemcpyAsync(d_sc, scores, (size_t)m * 4, cudaMemcpyHostToDevice, h->stream));
           p.stop(); }
@@ -392,10 +392,10 @@ y3_status y3_single_class_nms(y3_handle h, const float* boxes, const float* scor
         s.box = d_box; s.box_stride = 4; s.cls = d_sc; s.cls_stride = 1; s.obj = nullptr;
         s.rows_per_image = m; s.n_images = 1; s.nc = 1; s.raw_scores = true;
         NmsResult R;
-        { Phase p(h, &T.ms_nms); post_of(h)->enqueue(s, iou_thr); p.stop(); R = post_of(h)->finish(); }
+        { Phase p(h, &T.ms_nms, "y3:decode_nms_stitch"); post_of(h)->enqueue(s, iou_thr); p.stop(); R = post_of(h)->finish(); }
         *n_keep = R.n_kept;
         T.candidates = R.n_cand; T.kept = R.n_kept;
-        { Phase p(h, &T.ms_d2h);
+        { Phase p(h, &T.ms_d2h, "y3:d2h");
           from_device(h, keep, Y3_MEM_HOST, R.src_row, (size_t)R.n_kept * 4);
           p.stop(); }
         total.stop();
@@ -414,12 +414,12 @@ y3_status y3_per_class_nms(y3_handle h, const float* boxes, const float* obj, co
     if (n > 0) {
         y3_timings& T = h->timings;
         T = y3_timings{};
-        Phase total(h, &T.ms_total);
+        Phase total(h, &T.ms_total, "y3:total");
         h->stage_in.reserve((size_t)n * (5 + nc) * 4);
         float* d_box = h->stage_in.as<float>();
         float* d_obj = d_box + 4 * n;
         float* d_cls = d_obj + n;
-        { Phase p(h, &T.ms_h2d);
+        { Phase p(h, &T.ms_h2d, "y3:h2d");
           Y3_CUDA(cudaMemcpyAsync(d_box, boxes, (size_t)n * 16, cudaMemcpyHostToDevice, h->stream));
           Y3_CUDA(cudaMemcpyAsync(d_obj, obj, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
           Y3_CUDA(cudaMemcpyAsync(d_cls, cls, (size_t)n * nc * 4, cudaMemcpyHostToDevice, h->stream));
@@ -428,12 +428,12 @@ y3_status y3_per_class_nms(y3_handle h, const float* boxes, const float* obj, co
         s.box = d_box; s.box_stride = 4; s.obj = d_obj; s.obj_stride = 1; s.cls = d_cls; s.cls_stride = nc;
         s.rows_per_image = n; s.n_images = 1; s.nc = nc; s.score_thr = score_thr;
         NmsResult R;
-        { Phase p(h, &T.ms_nms); post_of(h)->enqueue(s, iou_thr); p.stop(); R = post_of(h)->finish(); }
+        { Phase p(h, &T.ms_nms, "y3:decode_nms_stitch"); post_of(h)->enqueue(s, iou_thr); p.stop(); R = post_of(h)->finish(); }
         *n_out = R.n_kept;
         T.candidates = R.n_cand; T.kept = R.n_kept;
         Y3_CHECK(R.n_kept <= cap, Y3_ERR_NOSPACE, "output capacity %lld < %lld kept boxes", (long long)cap, (long long)R.n_kept);
         if (R.n_kept) {
-            Phase p(h, &T.ms_d2h);
+            Phase p(h, &T.ms_d2h, "y3:d2h");
             Y3_CHECK(out_boxes && out_scores && out_labels, Y3_ERR_INVALID, "NULL output");
             from_device(h, out_boxes, Y3_MEM_HOST, R.boxes, (size_t)R.n_kept * 16);
             from_device(h, out_scores, Y3_MEM_HOST, R.scores, (size_t)R.n_kept * 4);
@@ -690,7 +690,7 @@ void infer_tiled_impl(y3_handle h, const void* img, y3_dtype dt, y3_mem img_mem,
     Y3_CHECK(tile_first >= 0 && tile_count >= 0 && tile_first + tile_count <= (int64_t)geo.size(), Y3_ERR_INVALID,
              "tile range [%lld,+%lld) outside 0..%zu", (long long)tile_first, (long long)tile_count, geo.size());
     y3_timings& Tm = h->timings;
-    Phase total(h, &Tm.ms_total);
+    Phase total(h, &Tm.ms_total, "y3:total");
     T->acc_rows = 0;
     *n_out = 0;
     if (tile_count > 0) {
@@ -735,12 +735,12 @@ void infer_tiled_impl(y3_handle h, const void* img, y3_dtype dt, y3_mem img_mem,
                 const CandSource src = heads_source(net, nb, true, min_box, score_thr, set);
                 sc.geo = d_geo + tile_first + t0;
                 bool done;
-                { Phase p(h, &Tm.ms_nms); done = seg && P->run_tiled(src, iou_thr, sc); p.stop(); }     // no host synchronisation
+                { Phase p(h, &Tm.ms_nms, "y3:decode_nms_stitch"); done = seg && P->run_tiled(src, iou_thr, sc); p.stop(); }     // no host synchronisation
                 if (!done) {
                     NmsResult R;
-                    { Phase p(h, &Tm.ms_nms); R = P->run(src, iou_thr); p.stop(); }
+                    { Phase p(h, &Tm.ms_nms, "y3:decode_nms_stitch"); R = P->run(src, iou_thr); p.stop(); }
                     Tm.candidates += R.n_cand; Tm.kept += R.n_kept;
-                    { Phase p(h, &Tm.ms_stitch); T->stitch(P, R, d_geo + tile_first + t0, S); p.stop(); }
+                    { Phase p(h, &Tm.ms_stitch, "y3:stitch"); T->stitch(P, R, d_geo + tile_first + t0, S); p.stop(); }
                 }
             } catch (...) {
                 h->stream = main_stream;
@@ -755,13 +755,13 @@ void infer_tiled_impl(y3_handle h, const void* img, y3_dtype dt, y3_mem img_mem,
             const TileGeo* g = d_geo + tile_first + t0;
             const int set = it & 1;
             {   // wait for this batch's rows, then start the next batch's upload so it overlaps this batch's compute
-                Phase p(h, &Tm.ms_h2d);
+                Phase p(h, &Tm.ms_h2d, "y3:h2d");
                 if (ready) Y3_CUDA(cudaStreamWaitEvent(h->stream, ready, 0));
                 p.stop();
                 if (t0 + nb < tile_count) ready = upload_rows_until(h, U, rows_needed(t0 + nb));
             }
-            { Phase p(h, &Tm.ms_prep); launch_tile_norm(h, d_img, dt, row_lo, (int)W, C, g, nb, th, tw, T->tiles.as<float>(), nullptr, T->sums.as<double>()); p.stop(); }
-            { Phase p(h, &Tm.ms_conv); net->forward(T->tiles.as<float>(), nb, set); p.stop(); }
+            { Phase p(h, &Tm.ms_prep, "y3:tile_slice_zscore"); launch_tile_norm(h, d_img, dt, row_lo, (int)W, C, g, nb, th, tw, T->tiles.as<float>(), nullptr, T->sums.as<double>()); p.stop(); }
+            { Phase p(h, &Tm.ms_conv, "y3:conv_stack"); net->forward(T->tiles.as<float>(), nb, set); p.stop(); }
             cudaEvent_t ev = take_event(h);
             Y3_CUDA(cudaEventRecord(ev, h->stream));
             heads_ready.push_back(ev);
@@ -782,7 +782,7 @@ void infer_tiled_impl(y3_handle h, const void* img, y3_dtype dt, y3_mem img_mem,
         for (cudaEvent_t e : heads_ready) h->event_pool.push_back(e);
         loop_phase.stop();
         release_upload(h, U);
-        { Phase p(h, &Tm.ms_d2h);
+        { Phase p(h, &Tm.ms_d2h, "y3:d2h");
           PostCtrl st{};
           finish_stitch(h, T, P, seg, preds, preds_mem, cap, n_out, &st);
           if (seg) { Tm.candidates = st.sum_cand; Tm.kept = st.sum_kept_nms; }
@@ -899,7 +899,7 @@ y3_status y3_infer_tiled_sharded(y3_handle h, const void* img, y3_dtype dt, y3_m
         for (auto& r_ : h->phase_log) { h->event_pool.push_back(r_.a); h->event_pool.push_back(r_.b); }
         h->phase_log.clear();
     }
-    Phase comm_phase(h, &Tm.ms_comm);
+    Phase comm_phase(h, &Tm.ms_comm, "y3:allgather");
     // 2. counts of every rank (a negative count flags an overflow)
     T->shard_counts.reserve((size_t)(world + 1) * 8);
     h->pin_small.reserve(1024);

@@ -10,6 +10,8 @@
 #include <map>
 #include <memory>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/yolo3_b200.h"
 
 namespace y3 {
@@ -117,20 +119,36 @@ inline cudaEvent_t take_event(y3_context* c) {
 }
 // Times a stage with two events on ctx->stream (whatever stream that is when start / stop run); nothing blocks
 // until flush_phases().
+// NVTX range on the host timeline (header-only NVTX3: a no-op unless a tool such as Nsight Systems is attached)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 struct Phase {
     y3_context* c;
     cudaEvent_t a;
     float* dst;
-    bool open = true;
-    Phase(y3_context* ctx, float* d) : c(ctx), a(take_event(ctx)), dst(d) { cudaEventRecord(a, c->stream); }
+    bool open = true, ranged = false;
+    // name (optional): the stage also becomes an NVTX range covering its enqueue
+    Phase(y3_context* ctx, float* d, const char* name = nullptr) : c(ctx), a(take_event(ctx)), dst(d) {
+        if (name) { nvtxRangePushA(name); ranged = true; }
+        cudaEventRecord(a, c->stream);
+    }
     void stop() {
         if (!open) return;
         open = false;
         cudaEvent_t b = take_event(c);
         cudaEventRecord(b, c->stream);
         c->phase_log.push_back({a, b, dst});
+        if (ranged) { nvtxRangePop(); ranged = false; }
     }
-    ~Phase() { if (open) c->event_pool.push_back(a); }
+    ~Phase() {
+        if (open) c->event_pool.push_back(a);
+        if (ranged) nvtxRangePop();
+    }
 };
 inline void flush_phases(y3_context* c) {
     cudaStreamSynchronize(c->stream);

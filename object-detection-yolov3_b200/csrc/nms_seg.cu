@@ -488,7 +488,7 @@ void PostProc::segmented_front(const CandSource& src, const KeyLayout& kl, int64
     bkeys.reserve((size_t)cap * 8);
     Y3_CUDA(cudaMemsetAsync(seg_cnt.p, 0, (size_t)(nseg + 1) * 4, st));
     {
-        Phase p(ctx, &ctx->timings.ms_decode);                  // decode + threshold + compaction kernel alone
+        Phase p(ctx, &ctx->timings.ms_decode, "y3:decode_threshold_compact");                  // decode + threshold + compaction kernel alone
         launch_candidates(src, kl, cap, true);
         p.stop();
     }

@@ -3,6 +3,7 @@
 // to the 1024-byte swizzle atom), and which `base_offset` makes it read what TMA wrote?
 // D[128 x 64] = A[rows s .. s+127][64] * I  for several row shifts s and both base_offset conventions.
 #include "common.cuh"
+#include "../../include/yolo3_b200_probe.h"
 #include "conv_tc.cuh"
 #include "ptx.cuh"
 

@@ -76,13 +76,35 @@ PROTOTYPES = {
     "y3_get_timings": (c_int32, [c_void_p, POINTER(Y3Timings)]),
     "y3_bench_forward": (c_int32, [c_void_p, c_int32, c_int32, POINTER(c_float)]),
     "y3_profile_layers": (c_int32, [c_void_p, c_int32, c_int32, c_char_p, c_int64]),
-    "y3_debug_umma_rowshift": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
-    "y3_debug_im2col": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
-                                  c_void_p, c_int32, c_void_p]),
     "y3_debug_layer_output": (c_int32, [c_void_p, c_char_p, c_int32, c_void_p, c_int64, POINTER(c_int32)]),
 }
 
+# include/yolo3_b200_probe.h - the hardware probes of tests/probe_*.py live in their own shared object
+PROBE_LIB_PATH = os.path.join(os.path.dirname(_HERE), "libyolo3_b200_probe.so")
+PROBE_PROTOTYPES = {
+    "y3_debug_umma_rowshift": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "y3_debug_im2col": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                  c_void_p, c_int32, c_void_p]),
+}
+
 _lib = None
+_probe = None
+
+
+def load_probe():
+    """libyolo3_b200_probe.so (test infrastructure): takes handles created by the main library."""
+    global _probe
+    if _probe is None:
+        load()
+        if not os.path.exists(PROBE_LIB_PATH):
+            raise RuntimeError("libyolo3_b200_probe.so not built - run `make -C object-detection-yolov3_b200 all`")
+        lib = ctypes.CDLL(PROBE_LIB_PATH)
+        for name, (res, args) in PROBE_PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _probe = lib
+    return _probe
 
 
 def load():
@@ -93,7 +115,7 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError("libyolo3_b200.so not built (%s) - run `python __graft_entry__.py` or "
                            "`make -C object-detection-yolov3_b200`; there is no fallback path" % LIB_PATH)
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res

@@ -3,6 +3,7 @@ import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "object-detection-yolov3_b200"))
+from yolo3_b200 import _lib  # noqa: E402
 from yolo3_b200 import post_engine
 from yolo3_b200._lib import check
 eng = post_engine(0)
@@ -54,7 +55,7 @@ for (N, H, W, C, stride, pad_lo, pad_hi) in [(3, 13, 13, 128, 1, 1, 1), (2, 12, 
     probes = np.array([c[:6] for c in cases], np.int32)
     out = np.zeros((len(cases), 128, 64), np.uint16)
     bits = bf16_bits(x)
-    check(eng.lib.y3_debug_im2col(eng.h, bits.ctypes.data, N, H, W, C, stride, pad_lo, pad_hi, 3, probes.ctypes.data, len(cases),
+    check(_lib.load_probe().y3_debug_im2col(eng.h, bits.ctypes.data, N, H, W, C, stride, pad_lo, pad_hi, 3, probes.ctypes.data, len(cases),
                                   out.ctypes.data), eng.h)
     bad = 0
     for i, c in enumerate(cases):

@@ -3,6 +3,7 @@ import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "object-detection-yolov3_b200"))
+from yolo3_b200 import _lib  # noqa: E402
 from yolo3_b200 import post_engine
 from yolo3_b200._lib import check
 eng = post_engine(0)
@@ -11,7 +12,7 @@ a = rng.integers(-64, 64, (512, 64)).astype(np.float32)          # exactly repre
 bits = (a.view(np.uint32) >> 16).astype(np.uint16)
 shifts = np.array([0, 1, 2, 3, 7, 8, 9, 130], np.int32)
 out = np.zeros((2, len(shifts), 128, 64), np.float32)
-check(eng.lib.y3_debug_umma_rowshift(eng.h, bits.ctypes.data, shifts.ctypes.data, len(shifts), out.ctypes.data), eng.h)
+check(_lib.load_probe().y3_debug_umma_rowshift(eng.h, bits.ctypes.data, shifts.ctypes.data, len(shifts), out.ctypes.data), eng.h)
 for v in range(2):
     for i, s in enumerate(shifts):
         ok = np.array_equal(out[v, i], a[s:s + 128])

@@ -8,8 +8,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    src = open(os.path.join(ROOT, "include", "yolo3_b200.h")).read()
+def declared_symbols(header="yolo3_b200.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(y3_[a-z0-9_]+)\s*\(", src)))
 
@@ -23,6 +23,16 @@ def test_header_symbols_exported():
         assert hasattr(lib, s), "missing export %s" % s
     assert sorted(_lib.PROTOTYPES) == syms, "ctypes prototypes out of sync with the header"
     assert lib.y3_abi_version() == _lib.ABI_VERSION == 3
+
+
+def test_probe_library_is_separate():
+    """the hardware probes of tests/probe_*.py are not in the product library"""
+    from yolo3_b200 import _lib
+    lib, probe = _lib.load(), _lib.load_probe()
+    syms = declared_symbols("yolo3_b200_probe.h")
+    assert sorted(_lib.PROBE_PROTOTYPES) == syms and len(syms) == 2
+    for s in syms:
+        assert hasattr(probe, s) and not hasattr(lib, s)
 
 
 def test_tile_plan_host_logic(golden):

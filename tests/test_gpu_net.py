@@ -248,3 +248,22 @@ def test_graph_replay_equals_eager_forward():
     got = eng.forward_heads(x[:1])
     want = mt.OracleNet(W2, (256, 256, 1), 1).feature_maps(torch.from_numpy(x[:1]))
     assert max(mt.heads_rel_err(a, b.numpy()) for a, b in zip(got, want)) <= HEAD_TOL
+
+
+def test_results_do_not_depend_on_stale_activations():
+    """Own bounds check (compute-sanitizer is closed on this pool): poison every activation buffer and image slot with a
+    full batch of 50x larger inputs, then run smaller batches - the heads must equal a fresh handle's, bit for bit.  A tile
+    that read rows of a neighbouring (stale) image slot, or a partial M tile leaking into valid rows, would show."""
+    from yolo3_b200 import Engine, weights
+    w = weights.random_init(1, 1, 3, seed=0, randomize_bn=True)
+    x = np.random.default_rng(0).standard_normal((6, 1, 512, 512)).astype(np.float32)
+    fresh = Engine((512, 512, 1), 1, None, max_batch=6)
+    fresh.load_weights(w)
+    want = {b: [h.copy() for h in fresh.forward_heads(x[:b])] for b in (1, 3, 5)}
+    fresh.close()
+    eng = Engine((512, 512, 1), 1, None, max_batch=6)
+    eng.load_weights(w)
+    for b in (1, 3, 5):
+        eng.forward_heads(x * 50.0)
+        got = eng.forward_heads(x[:b])
+        assert all(np.array_equal(p, q) for p, q in zip(got, want[b])), "batch %d depends on stale buffers" % b
