@@ -39,11 +39,14 @@ struct CandOut {
     int64_t cap;
     int* seg_cnt;
     uint32_t* slot;
+    float4* box;          // optional: the candidate's decoded box (already computed for the small-box filter), so that the
+                          // NMS kernels of the segmented pipeline load 16 bytes instead of decoding the row again
 };
 
 // All 32 lanes call this (converged); lanes with `pass` append (key, val).  One atomic per warp for the list position
 // and one per distinct segment among the passing lanes (match-any aggregation) for the slot.
-__device__ __forceinline__ void emit_candidates(const CandOut& O, bool pass, uint64_t key, uint32_t val, uint32_t seg, int lane) {
+__device__ __forceinline__ void emit_candidates(const CandOut& O, bool pass, uint64_t key, uint32_t val, uint32_t seg, int lane,
+                                                const float4 bx = make_float4(0.f, 0.f, 0.f, 0.f)) {
     const unsigned m = __ballot_sync(0xffffffffu, pass);
     if (!m) return;
     unsigned long long base = 0;
@@ -65,6 +68,7 @@ __device__ __forceinline__ void emit_candidates(const CandOut& O, bool pass, uin
             O.keys[pos] = key;
             O.vals[pos] = val;
             if (O.slot) O.slot[pos] = sl;
+            if (O.box) O.box[pos] = bx;
         }
     }
 }
@@ -88,6 +92,7 @@ k_candidates(CandSource src, KeyLayout kl, int64_t total, float logit_floor, Can
         bool pass = false;
         uint64_t key = 0;
         uint32_t val = 0, seg = 0;
+        float4 cbox = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e < (IDX)total) {
             const IDX grow = e / nc;                         // global row = img * rows + row
             const int c = (int)(e - grow * nc);
@@ -106,9 +111,9 @@ k_candidates(CandSource src, KeyLayout kl, int64_t total, float logit_floor, Can
                     const float p = sigmoid_f(lc);
                     s = __fsqrt_rn(__fmul_rn(p, o));
                     pass = (s >= thr);
-                    if (pass && src.filter_small) {
-                        const float4 bx = decode_box(src.dec, hp, sc, cell, a);
-                        pass = (__fsub_rn(bx.z, bx.x) > src.min_size) && (__fsub_rn(bx.w, bx.y) > src.min_size);
+                    if (pass && (src.filter_small || O.box)) {
+                        cbox = decode_box(src.dec, hp, sc, cell, a);
+                        if (src.filter_small) pass = (__fsub_rn(cbox.z, cbox.x) > src.min_size) && (__fsub_rn(cbox.w, cbox.y) > src.min_size);
                     }
                 }
             } else {
@@ -121,11 +126,10 @@ k_candidates(CandSource src, KeyLayout kl, int64_t total, float logit_floor, Can
                     s = __fsqrt_rn(__fmul_rn(p, o));             // np.sqrt(class_probs * objectness)
                     pass = (s >= thr);                           // NaN -> false
                 }
-                if (pass && src.filter_small) {
+                if (pass && (src.filter_small || O.box)) {
                     const float* b = src.box + (int64_t)grow * src.box_stride;
-                    const float w = __fsub_rn(__ldg(b + 2), __ldg(b + 0));
-                    const float h = __fsub_rn(__ldg(b + 3), __ldg(b + 1));
-                    pass = (w > src.min_size) && (h > src.min_size);
+                    cbox = make_float4(__ldg(b + 0), __ldg(b + 1), __ldg(b + 2), __ldg(b + 3));
+                    if (src.filter_small) pass = (__fsub_rn(cbox.z, cbox.x) > src.min_size) && (__fsub_rn(cbox.w, cbox.y) > src.min_size);
                 }
             }
             if (pass && src.row_seg) {
@@ -138,7 +142,7 @@ k_candidates(CandSource src, KeyLayout kl, int64_t total, float logit_floor, Can
                 val = (uint32_t)grow;
             }
         }
-        emit_candidates(O, pass, key, val, seg, lane);
+        emit_candidates(O, pass, key, val, seg, lane, cbox);
     }
 }
 
@@ -164,6 +168,7 @@ k_candidates_heads1(CandSource src, KeyLayout kl, float logit_floor, CandOut O) 
         bool pass = false;
         float s = 0.f;
         uint32_t img = 0, row = 0;
+        float4 cbox = make_float4(0.f, 0.f, 0.f, 0.f);
         if (grow < rows_total) {
             img = grow / rpi;
             row = grow - img * rpi;
@@ -175,14 +180,14 @@ k_candidates_heads1(CandSource src, KeyLayout kl, float logit_floor, CandOut O) 
                 if (lc >= logit_floor) {
                     s = __fsqrt_rn(__fmul_rn(sigmoid_f(lc), sigmoid_f(lo)));
                     pass = (s >= thr);
-                    if (pass && src.filter_small) {
-                        const float4 bx = decode_box(src.dec, hp, sc, cell, a);
-                        pass = (__fsub_rn(bx.z, bx.x) > src.min_size) && (__fsub_rn(bx.w, bx.y) > src.min_size);
+                    if (pass && (src.filter_small || O.box)) {
+                        cbox = decode_box(src.dec, hp, sc, cell, a);
+                        if (src.filter_small) pass = (__fsub_rn(cbox.z, cbox.x) > src.min_size) && (__fsub_rn(cbox.w, cbox.y) > src.min_size);
                     }
                 }
             }
         }
-        emit_candidates(O, pass, make_key(kl, img, s, row), grow, img, lane);
+        emit_candidates(O, pass, make_key(kl, img, s, row), grow, img, lane, cbox);
     }
 }
 
@@ -230,7 +235,8 @@ k_candidates_rows(CandSource src, KeyLayout kl, float logit_floor, const uint32_
         int sc, cell, a;
         const float* hp = head_row(src.dec, (int)img, (int)row, &sc, &cell, &a);
         const float o = sigmoid_f(__ldg(hp + 4));
-        bool size_known = !src.filter_small, size_ok = true;
+        bool size_known = false, size_ok = true;
+        float4 cbox = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int c00 = 0; c00 < nc; c00 += 32 * ROW_IT) {
             float lc[ROW_IT];
 #pragma unroll
@@ -254,8 +260,8 @@ k_candidates_rows(CandSource src, KeyLayout kl, float logit_floor, const uint32_
             }
             if (!any) continue;
             if (!size_known) {                                   // warp-uniform: every lane evaluates the same box
-                const float4 bx = decode_box(src.dec, hp, sc, cell, a);
-                size_ok = (__fsub_rn(bx.z, bx.x) > src.min_size) && (__fsub_rn(bx.w, bx.y) > src.min_size);
+                cbox = decode_box(src.dec, hp, sc, cell, a);
+                if (src.filter_small) size_ok = (__fsub_rn(cbox.z, cbox.x) > src.min_size) && (__fsub_rn(cbox.w, cbox.y) > src.min_size);
                 size_known = true;
             }
             if (!size_ok) break;                                 // the whole row is dropped by filter_small_boxes
@@ -277,6 +283,7 @@ k_candidates_rows(CandSource src, KeyLayout kl, float logit_floor, const uint32_
                         O.keys[pos] = make_key(kl, seg, s[it], row);
                         O.vals[pos] = grow;
                         if (O.slot) O.slot[pos] = sl;
+                        if (O.box) O.box[pos] = cbox;
                     }
                 }
                 before += __popc(pm[it]);
@@ -745,11 +752,13 @@ void PostProc::launch_candidates(const CandSource& src, const KeyLayout& kl, int
     vals[0].reserve(cap * 4);
     counters.reserve(64);
     Y3_CUDA(cudaMemsetAsync(counters.p, 0, 64, st));
-    CandOut O{keys[0].as<uint64_t>(), vals[0].as<uint32_t>(), counters.as<unsigned long long>(), cap, nullptr, nullptr};
+    CandOut O{keys[0].as<uint64_t>(), vals[0].as<uint32_t>(), counters.as<unsigned long long>(), cap, nullptr, nullptr, nullptr};
     if (count_segments) {
         slot.reserve(cap * 4);
+        cbox.reserve(cap * 16);
         O.seg_cnt = seg_cnt.as<int>();
         O.slot = slot.as<uint32_t>();
+        O.box = cbox.as<float4>();
     }
     // logit(thr^2) minus a margin far above any rounding of expf / the division (see k_candidates)
     float logit_floor = -INFINITY;

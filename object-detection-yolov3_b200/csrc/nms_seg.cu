@@ -136,12 +136,15 @@ k2_scan(const int* __restrict__ seg_cnt, int nseg, int* __restrict__ seg_off, in
 }
 
 __global__ void __launch_bounds__(256)
-k2_bin(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ slot, const int* __restrict__ seg_off, int seg_shift,
-       const PostCtrl* __restrict__ C, uint64_t* __restrict__ bkeys) {
+k2_bin(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ slot, const float4* __restrict__ cbox,
+       const int* __restrict__ seg_off, int seg_shift, const PostCtrl* __restrict__ C, uint64_t* __restrict__ bkeys,
+       float4* __restrict__ bbox) {
     const int K = C->K;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < K; p += gridDim.x * blockDim.x) {
         const uint64_t key = keys[p];
-        bkeys[seg_off[(int)(key >> seg_shift)] + (int)slot[p]] = key;
+        const int dst = seg_off[(int)(key >> seg_shift)] + (int)slot[p];
+        bkeys[dst] = key;
+        bbox[dst] = cbox[p];
     }
 }
 
@@ -154,6 +157,7 @@ struct SegArgs {
     int tiled;
     const TileGeo* geo;
     StitchArgs S;
+    const float4* bbox;       // decoded boxes of the binned candidates (same positions as bkeys until a CTA sorts its segment)
 };
 
 template <int PL>
@@ -167,7 +171,6 @@ __device__ __forceinline__ void warp_select_nms(const SegArgs& A, const uint64_t
     float4 b[PL];
     float a[PL];
     unsigned alive = 0, odd = 0;                                 // odd: a non-finite coordinate / area -> exact IoU path
-    const int img = A.src.seg_image(seg);
     const bool thr_plain = A.thr > 0.f && A.thr < 1e30f;
 #pragma unroll
     for (int k = 0; k < PL; ++k) {
@@ -177,14 +180,14 @@ __device__ __forceinline__ void warp_select_nms(const SegArgs& A, const uint64_t
         a[k] = 0.f;
         if (j < m) {
             sub[k] = bkeys[s0 + j] & sub_mask;
-            b[k] = cand_box(A.src, img, (int64_t)(sub[k] & A.kl.row_mask));
+            b[k] = A.bbox[s0 + j];
             a[k] = box_area_exact(b[k]);
             alive |= 1u << k;
             if (!thr_plain || !box_is_plain(b[k], a[k])) odd |= 1u << k;
         }
     }
     TileGeo g{};
-    if (A.tiled) g = A.geo[img];
+    if (A.tiled) g = A.geo[A.src.seg_image(seg)];
     int t = 0, tn = 0;
     while (true) {
         uint64_t best = ~0ull;
@@ -467,6 +470,7 @@ static SegArgs seg_args(const CandSource& src, const KeyLayout& kl, float thr, c
     A.tiled = st ? 1 : 0;
     A.geo = st ? st->geo : nullptr;
     A.S = st ? st->S : StitchArgs{};
+    A.bbox = nullptr;
     return A;
 }
 
@@ -485,7 +489,7 @@ void PostProc::segmented_front(const CandSource& src, const KeyLayout& kl, int64
     seg_cnt.reserve((size_t)(nseg + 1) * 4); seg_off32.reserve((size_t)(nseg + 1) * 4);
     mid_list.reserve((size_t)nseg * 4); kept_cnt.reserve((size_t)nseg * 4);
     out_off.reserve((size_t)(nseg + 1) * 4);
-    bkeys.reserve((size_t)cap * 8);
+    bkeys.reserve((size_t)cap * 8); bbox.reserve((size_t)cap * 16);
     Y3_CUDA(cudaMemsetAsync(seg_cnt.p, 0, (size_t)(nseg + 1) * 4, st));
     {
         Phase p(ctx, &ctx->timings.ms_decode, "y3:decode_threshold_compact");                  // decode + threshold + compaction kernel alone
@@ -495,15 +499,16 @@ void PostProc::segmented_front(const CandSource& src, const KeyLayout& kl, int64
     k2_scan<<<1, 1024, 0, st>>>(seg_cnt.as<int>(), nseg, seg_off32.as<int>(), mid_list.as<int>(), kept_cnt.as<int>(),
                                 counters.as<unsigned long long>(), (long long)cap, ctrl.as<PostCtrl>());
     Y3_LAUNCHED(ctx);
-    k2_bin<<<ctx->sm_count * 4, 256, 0, st>>>(keys[0].as<uint64_t>(), slot.as<uint32_t>(), seg_off32.as<int>(), kl.seg_shift,
-                                              ctrl.as<PostCtrl>(), bkeys.as<uint64_t>());
+    k2_bin<<<ctx->sm_count * 4, 256, 0, st>>>(keys[0].as<uint64_t>(), slot.as<uint32_t>(), cbox.as<float4>(), seg_off32.as<int>(), kl.seg_shift,
+                                              ctrl.as<PostCtrl>(), bkeys.as<uint64_t>(), bbox.as<float4>());
     Y3_LAUNCHED(ctx);
 }
 
 void PostProc::segmented_nms(const CandSource& src, const KeyLayout& kl, float iou_thr, const StitchCtx* stc) {
     cudaStream_t st = ctx->stream;
     const int64_t cap = capacity(src);
-    const SegArgs A = seg_args(src, kl, iou_thr, stc);
+    SegArgs A = seg_args(src, kl, iou_thr, stc);
+    A.bbox = bbox.as<float4>();
     rbox.reserve((size_t)cap * 16); rkey.reserve((size_t)cap * 8);
     sbox.reserve((size_t)cap * 16); sarea.reserve((size_t)cap * 4); supp.reserve((size_t)cap); keepf.reserve((size_t)cap);
     PostCtrl* C = ctrl.as<PostCtrl>();

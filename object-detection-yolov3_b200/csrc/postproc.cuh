@@ -95,7 +95,7 @@ struct PostProc {
     DevBuf keys[2], vals[2], sort_tmp, sbox, sarea, supp, keepf, seg_off, counters, blk, kbuf;
     DevBuf o_box, o_score, o_label, o_img, o_src, o_rank;
     // segmented pipeline (nms_seg.cu)
-    DevBuf slot, seg_cnt, seg_off32, bkeys, rbox, rkey, kept_cnt, out_off, mid_list, ctrl, live;
+    DevBuf slot, seg_cnt, seg_off32, bkeys, rbox, rkey, kept_cnt, out_off, mid_list, ctrl, live, cbox, bbox;
     PinnedBuf host_small, host_ctrl;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_cand_ms = 0.f;    // device time of the last candidates launch of the global-sort path
