@@ -9,6 +9,8 @@
 #include <vector>
 #include <map>
 #include <memory>
+#include <utility>
+#include <stdlib.h>
 
 #include <nvtx3/nvToolsExt.h>
 
@@ -160,6 +162,28 @@ inline void flush_phases(y3_context* c) {
     }
     c->phase_log.clear();
     cudaGetLastError();
+}
+
+// ---- programmatic dependent launch for chains of short kernels (the post-processing pipeline): the next kernel of the
+// stream may be scheduled while the current one drains; every chained kernel starts with pdl_chain_sync(), which waits
+// until the grids it depends on have completed (memory visible) and then lets ITS successor be scheduled.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_chain_sync() {
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+}
+#endif
+template <typename... KArgs, typename... Args>
+inline void launch_chained(y3_context* ctx, void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
+    static const bool pdl = getenv("Y3_NO_POST_PDL") == nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    Y3_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+    count_launch(ctx);
 }
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

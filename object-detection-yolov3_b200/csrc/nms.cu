@@ -157,6 +157,7 @@ k_candidates(CandSource src, KeyLayout kl, int64_t total, float logit_floor, Can
 //                 cluster spatially, so a few warps did most of the work serially - 18 % warps active, 0.10 ms on K2.)
 __global__ void __launch_bounds__(256)
 k_candidates_heads1(CandSource src, KeyLayout kl, float logit_floor, CandOut O) {
+    pdl_chain_sync();
     const int lane = threadIdx.x & 31;
     const uint32_t rpi = (uint32_t)src.rows_per_image;
     const uint32_t rows_total = rpi * (uint32_t)src.n_images;
@@ -193,6 +194,7 @@ k_candidates_heads1(CandSource src, KeyLayout kl, float logit_floor, CandOut O) 
 
 __global__ void __launch_bounds__(256)
 k_live_rows(CandSource src, float logit_floor, uint32_t* __restrict__ live, unsigned int* __restrict__ n_live) {
+    pdl_chain_sync();
     const int lane = threadIdx.x & 31;
     const uint32_t rpi = (uint32_t)src.rows_per_image;
     const uint32_t rows_total = rpi * (uint32_t)src.n_images;
@@ -222,6 +224,7 @@ static constexpr int ROW_IT = 4;     // class chunks of 32 handled per emission 
 __global__ void __launch_bounds__(256)
 k_candidates_rows(CandSource src, KeyLayout kl, float logit_floor, const uint32_t* __restrict__ live,
                   const unsigned int* __restrict__ n_live, CandOut O) {
+    pdl_chain_sync();
     const int lane = threadIdx.x & 31;
     const uint32_t rpi = (uint32_t)src.rows_per_image;
     const uint32_t warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -771,13 +774,15 @@ void PostProc::launch_candidates(const CandSource& src, const KeyLayout& kl, int
     if (row_kernel && src.from_heads && total + 32 < (1ll << 32)) {
         const int rblocks = (int)std::min<int64_t>((rows + 255) / 256, (int64_t)ctx->sm_count * 8);
         if (src.nc == 1) {
-            k_candidates_heads1<<<rblocks, 256, 0, st>>>(src, kl, logit_floor, O);
+            launch_chained(ctx, k_candidates_heads1, rblocks, 256, 0, st, src, kl, logit_floor, O);
+            return;
         } else {
             live.reserve((size_t)rows * 4);
             unsigned int* n_live = reinterpret_cast<unsigned int*>(counters.as<unsigned char>() + 16);     // zeroed above
-            k_live_rows<<<rblocks, 256, 0, st>>>(src, logit_floor, live.as<uint32_t>(), n_live);
-            Y3_LAUNCHED(ctx);
-            k_candidates_rows<<<ctx->sm_count * 8, 256, 0, st>>>(src, kl, logit_floor, live.as<uint32_t>(), n_live, O);
+            launch_chained(ctx, k_live_rows, rblocks, 256, 0, st, src, logit_floor, live.as<uint32_t>(), n_live);
+            launch_chained(ctx, k_candidates_rows, ctx->sm_count * 8, 256, 0, st, src, kl, logit_floor, (const uint32_t*)live.as<uint32_t>(),
+                           (const unsigned int*)n_live, O);
+            return;
         }
     } else if (total + 32 < (1ll << 32)) {
         k_candidates<uint32_t><<<blocks, 256, 0, st>>>(src, kl, total, logit_floor, O);

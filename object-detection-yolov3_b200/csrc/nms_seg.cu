@@ -79,6 +79,7 @@ __device__ __forceinline__ int size_class(int c) {
 __global__ void __launch_bounds__(1024)
 k2_scan(const int* __restrict__ seg_cnt, int nseg, int* __restrict__ seg_off, int* __restrict__ work_list,
         int* __restrict__ kept_cnt, const unsigned long long* __restrict__ counter, long long cap, PostCtrl* __restrict__ C) {
+    pdl_chain_sync();
     __shared__ int s_warp[33];
     __shared__ int s_cls[N_CLS], s_cls_off[N_CLS], s_max;
     const int tid = threadIdx.x;
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(256)
 k2_bin(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ slot, const float4* __restrict__ cbox,
        const int* __restrict__ seg_off, int seg_shift, const PostCtrl* __restrict__ C, uint64_t* __restrict__ bkeys,
        float4* __restrict__ bbox) {
+    pdl_chain_sync();
     const int K = C->K;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < K; p += gridDim.x * blockDim.x) {
         const uint64_t key = keys[p];
@@ -242,6 +244,7 @@ __device__ __forceinline__ void warp_select_nms(const SegArgs& A, const uint64_t
 __global__ void __launch_bounds__(256, K2_WARP_MINB)
 k2_nms_warp(const SegArgs A, const uint64_t* __restrict__ bkeys, const int* __restrict__ seg_off, const int* __restrict__ work_list,
             float4* __restrict__ rbox, uint64_t* __restrict__ rkey, int* __restrict__ kept_cnt, PostCtrl* __restrict__ C) {
+    pdl_chain_sync();
     __shared__ int s_nms;
     const int lane = threadIdx.x & 31;
     const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -305,6 +308,7 @@ k2_nms_cta(const SegArgs A, uint64_t* __restrict__ bkeys, const int* __restrict_
            int* __restrict__ cursor, const int* __restrict__ range_end,
            float4* __restrict__ sbox, float* __restrict__ sarea, uint8_t* __restrict__ supp, uint8_t* __restrict__ keepf,
            float4* __restrict__ rbox, uint64_t* __restrict__ rkey, int* __restrict__ kept_cnt, PostCtrl* __restrict__ C) {
+    pdl_chain_sync();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem_raw);       // sort phase
     ChunkSmem& S = *reinterpret_cast<ChunkSmem*>(smem_raw);          // NMS phase (the keys are in global memory again by then)
@@ -398,6 +402,7 @@ k2_nms_cta(const SegArgs A, uint64_t* __restrict__ bkeys, const int* __restrict_
 // ------------------------------------------------------------------------------------------ output
 __global__ void __launch_bounds__(1024)
 k2_out_scan(const int* __restrict__ kept_cnt, int nseg, int* __restrict__ out_off, PostCtrl* __restrict__ C, int tiled) {
+    pdl_chain_sync();
     __shared__ int s_warp[33];
     const int tid = threadIdx.x;
     const int per = (nseg + 1023) / 1024;
@@ -424,6 +429,7 @@ __global__ void __launch_bounds__(256)
 k2_emit(const SegArgs A, const int* __restrict__ seg_off, const int* __restrict__ kept_cnt, const int* __restrict__ out_off,
         const float4* __restrict__ rbox, const uint64_t* __restrict__ rkey, const PostCtrl* __restrict__ C, EmitPlain P,
         double* __restrict__ preds, long long cap_rows) {
+    pdl_chain_sync();
     const int lane = threadIdx.x & 31;
     const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -496,12 +502,10 @@ void PostProc::segmented_front(const CandSource& src, const KeyLayout& kl, int64
         launch_candidates(src, kl, cap, true);
         p.stop();
     }
-    k2_scan<<<1, 1024, 0, st>>>(seg_cnt.as<int>(), nseg, seg_off32.as<int>(), mid_list.as<int>(), kept_cnt.as<int>(),
-                                counters.as<unsigned long long>(), (long long)cap, ctrl.as<PostCtrl>());
-    Y3_LAUNCHED(ctx);
-    k2_bin<<<ctx->sm_count * 4, 256, 0, st>>>(keys[0].as<uint64_t>(), slot.as<uint32_t>(), cbox.as<float4>(), seg_off32.as<int>(), kl.seg_shift,
-                                              ctrl.as<PostCtrl>(), bkeys.as<uint64_t>(), bbox.as<float4>());
-    Y3_LAUNCHED(ctx);
+    launch_chained(ctx, k2_scan, 1, 1024, 0, st, seg_cnt.as<int>(), nseg, seg_off32.as<int>(), mid_list.as<int>(), kept_cnt.as<int>(),
+                   counters.as<unsigned long long>(), (long long)cap, ctrl.as<PostCtrl>());
+    launch_chained(ctx, k2_bin, ctx->sm_count * 4, 256, 0, st, keys[0].as<uint64_t>(), slot.as<uint32_t>(), cbox.as<float4>(), seg_off32.as<int>(),
+                   kl.seg_shift, ctrl.as<PostCtrl>(), bkeys.as<uint64_t>(), bbox.as<float4>());
 }
 
 void PostProc::segmented_nms(const CandSource& src, const KeyLayout& kl, float iou_thr, const StitchCtx* stc) {
@@ -546,18 +550,15 @@ void PostProc::segmented_nms(const CandSource& src, const KeyLayout& kl, float i
     }
     {
         const int blocks = std::min((A.nseg + 7) / 8, ctx->sm_count * K2_WARP_MINB);
-        k2_nms_warp<<<blocks, 256, 0, st>>>(A, bkeys.as<uint64_t>(), seg_off32.as<int>(), mid_list.as<int>(), rbox.as<float4>(),
-                                            rkey.as<uint64_t>(), kept_cnt.as<int>(), C);
-        Y3_LAUNCHED(ctx);
+        launch_chained(ctx, k2_nms_warp, blocks, 256, 0, st, A, bkeys.as<uint64_t>(), seg_off32.as<int>(), mid_list.as<int>(), rbox.as<float4>(),
+                       rkey.as<uint64_t>(), kept_cnt.as<int>(), C);
     }
     if (cta_possible) Y3_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
-    k2_out_scan<<<1, 1024, 0, st>>>(kept_cnt.as<int>(), A.nseg, out_off.as<int>(), ctrl.as<PostCtrl>(), A.tiled);
-    Y3_LAUNCHED(ctx);
+    launch_chained(ctx, k2_out_scan, 1, 1024, 0, st, kept_cnt.as<int>(), A.nseg, out_off.as<int>(), ctrl.as<PostCtrl>(), A.tiled);
     if (stc) {
         const int blocks = std::min((A.nseg + 7) / 8, ctx->sm_count * 8);
-        k2_emit<<<blocks, 256, 0, st>>>(A, seg_off32.as<int>(), kept_cnt.as<int>(), out_off.as<int>(), rbox.as<float4>(), rkey.as<uint64_t>(),
-                                        ctrl.as<PostCtrl>(), EmitPlain{}, stc->preds, (long long)stc->cap_rows);
-        Y3_LAUNCHED(ctx);
+        launch_chained(ctx, k2_emit, blocks, 256, 0, st, A, seg_off32.as<int>(), kept_cnt.as<int>(), out_off.as<int>(), rbox.as<float4>(),
+                       rkey.as<uint64_t>(), ctrl.as<PostCtrl>(), EmitPlain{}, stc->preds, (long long)stc->cap_rows);
     }
 }
 
@@ -570,9 +571,8 @@ void PostProc::segmented_emit_plain(const CandSource& src, const KeyLayout& kl) 
     const SegArgs A = seg_args(src, kl, 0.f, nullptr);
     EmitPlain P{o_box.as<float4>(), o_score.as<float>(), o_label.as<int32_t>(), o_img.as<int32_t>(), o_src.as<int32_t>()};
     const int blocks = std::min((A.nseg + 7) / 8, ctx->sm_count * 8);
-    k2_emit<<<blocks, 256, 0, st>>>(A, seg_off32.as<int>(), kept_cnt.as<int>(), out_off.as<int>(), rbox.as<float4>(), rkey.as<uint64_t>(),
-                                    ctrl.as<PostCtrl>(), P, nullptr, 0);
-    Y3_LAUNCHED(ctx);
+    launch_chained(ctx, k2_emit, blocks, 256, 0, st, A, seg_off32.as<int>(), kept_cnt.as<int>(), out_off.as<int>(), rbox.as<float4>(),
+                   rkey.as<uint64_t>(), ctrl.as<PostCtrl>(), P, (double*)nullptr, (long long)0);
     host_ctrl.reserve(sizeof(PostCtrl));
     Y3_CUDA(cudaMemcpyAsync(host_ctrl.p, ctrl.p, sizeof(PostCtrl), cudaMemcpyDeviceToHost, st));
     pending_cap = cap;
