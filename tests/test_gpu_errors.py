@@ -76,3 +76,41 @@ def test_empty_inputs(eng):
     b, s, l = bbox_utils.per_class_nms(np.zeros((5, 4), np.float32), np.zeros((5, 1), np.float32), np.zeros((5, 2), np.float32))
     assert b is None and s is None and l is None                             # the reference's (None, None, None)
     assert bbox_utils.filter_small_boxes(np.zeros((0, 7), np.float32), 3).shape == (0, 7)
+
+
+def test_round2_entry_points_check_state_and_arguments(eng):
+    """y3_infer_tiled_sharded before y3_comm_init, y3_detect_image with a foreign size, y3_cross_seam_nms with bad arguments,
+    a candidate capacity overflow in the segmented pipeline: status + message, and the handle stays usable"""
+    from yolo3_b200 import Engine, Y3Error, _lib, weights
+    img = np.zeros((200, 230, 3), np.uint8)
+    with pytest.raises(Y3Error) as ex:
+        eng.infer_tiled_sharded(img, (96, 128), 8, edge_range=32)
+    assert ex.value.code == _lib.ERR_STATE and "y3_comm_init" in str(ex.value)
+    with pytest.raises(Y3Error) as ex:
+        eng.detect_image(np.zeros((64, 64, 3), np.uint8))
+    assert ex.value.code == _lib.ERR_INVALID and "network input" in str(ex.value)
+    n = ctypes.c_int64()
+    st = eng.lib.y3_cross_seam_nms(eng.h, None, 0, 5, 2, 100, 100, 32, 32, 0, ctypes.c_float(0.3), None, 0, 0, ctypes.byref(n))
+    assert st == _lib.ERR_INVALID
+    assert eng.lib.y3_comm_unique_id(None) == _lib.ERR_INVALID
+    p = ctypes.c_void_p()
+    assert eng.lib.y3_host_alloc(0, ctypes.byref(p)) == _lib.ERR_INVALID
+    # candidate list overflow: every (row, class) passes but the handle was created with room for 100 candidates
+    small = Engine(SIZE, 2, None, max_batch=1, max_candidates=100)
+    w = weights.random_init(3, 2, 3, seed=0, randomize_bn=True)
+    for i in (1, 2, 3):
+        b = np.zeros((3, 7), np.float32)
+        b[:, 4:] = 9.0                                   # objectness and class logits far above the threshold
+        w["feature_map_%d/bias" % i] = b.reshape(-1)
+        w["feature_map_%d/kernel" % i] = np.zeros_like(w["feature_map_%d/kernel" % i])
+    small.load_weights(w)
+    with pytest.raises(Y3Error) as ex:
+        small.detect(np.zeros((1, 3, 96, 128), np.float32), 0, 0.3, 0.1)
+    assert ex.value.code == _lib.ERR_NOSPACE and "max_candidates" in str(ex.value)
+    with pytest.raises(Y3Error) as ex:
+        small.infer_tiled(np.zeros((96, 128, 3), np.uint8), (96, 128), 0, edge_range=32)
+    assert ex.value.code == _lib.ERR_NOSPACE
+    # the first handle still works
+    assert eng.forward_heads(np.zeros((1, 3, 96, 128), np.float32))[0].shape == (1, 21, 3, 4)
+    b, s, l = eng.detect_image(np.zeros(SIZE, np.uint8))
+    assert b.shape[1] == 4 and len(s) == len(l) == len(b)
