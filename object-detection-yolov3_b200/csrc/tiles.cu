@@ -13,6 +13,7 @@
 //   ghost-band ownership by box centre, origin add (fp32), np.round (half-to-even) -> int32,
 //   centre-inside-image filter, clamp to [0, size-1]; ordered compaction keeps the reference's order.
 #include "tiles.cuh"
+#include <stdlib.h>
 
 namespace y3 {
 
@@ -328,6 +329,10 @@ int64_t Tiler::cross_seam(PostProc* post, const double* preds_dev, int64_t n, co
     k_seam_prepare<<<ceil_div(n, 256), 256, 0, st>>>(preds_dev, n, zone_y, zone_x, seam_box.as<float4>(), seam_score.as<float>(),
                                                      seam_label.as<int32_t>(), seam_cand.as<uint8_t>(), seam_keep.as<uint8_t>());
     Y3_LAUNCHED(ctx);
+    static const bool use_grid = getenv("Y3_SEAM_SERIAL") == nullptr;
+    const bool fast = use_grid && cross_seam_grid(seam_box.as<float4>(), seam_score.as<float>(), seam_label.as<int32_t>(),
+                                                  seam_cand.as<uint8_t>(), n, S, iou_thr, seam_keep.as<uint8_t>());
+    if (!fast) {
     CandSource src;
     src.box = seam_box.as<float>(); src.box_stride = 4;
     src.cls = seam_score.as<float>(); src.cls_stride = 1; src.obj = nullptr;
@@ -337,6 +342,7 @@ int64_t Tiler::cross_seam(PostProc* post, const double* preds_dev, int64_t n, co
     if (R.n_kept > 0) {
         k_seam_mark<<<ceil_div(R.n_kept, 256), 256, 0, st>>>(R.src_row, R.n_kept, seam_keep.as<uint8_t>());
         Y3_LAUNCHED(ctx);
+    }
     }
     const int64_t total = post->flag_offsets(seam_keep.as<uint8_t>(), n);
     if (total > 0) {

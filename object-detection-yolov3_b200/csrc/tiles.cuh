@@ -18,6 +18,8 @@ struct Tiler {
     DevBuf geo, img, tiles, ibox, flags, acc, dets, sums;
     DevBuf seam_box, seam_score, seam_label, seam_cand, seam_keep, seam_out;      // cross-seam stage
     DevBuf shard_local, shard_gather, shard_counts;                               // sharded path (comm.cu)
+    PinnedBuf grid_host;
+    DevBuf grid_ctrl, grid_cells, grid_slot, grid_members, grid_state, grid_dom, grid_ndom;   // sparse parallel NMS (nms_grid.cu)
     DevBuf geo1;                                                                  // one "tile" = the whole image (y3_detect_image)
     bool geo1_ready = false;
     int geo1_h = 0, geo1_w = 0;
@@ -30,6 +32,9 @@ struct Tiler {
     // a zone boundary of the tile grid; suppressed rows are dropped, order kept.  preds_dev [n,6] float64 on the device
     // -> seam_out (device), returns the surviving row count.  Synchronises the stream.
     int64_t cross_seam(PostProc* post, const double* preds_dev, int64_t n, const StitchArgs& S, int nc, float iou_thr);
+    // sparse fast path of the stage (nms_grid.cu); false = not applicable, use the general pipeline
+    bool cross_seam_grid(const float4* box, const float* score, const int32_t* label, const uint8_t* cand, int64_t n,
+                         const StitchArgs& S, float iou_thr, uint8_t* keepm);
 };
 
 }  // namespace y3

@@ -156,3 +156,39 @@ def test_bench_workload_parity_2048_crop():
     errs = [mt.heads_rel_err(a, b.numpy()) for a, b in zip(got, ref)]
     print("head errors on sampled tiles", errs)
     assert max(errs) <= 2e-2, errs
+
+
+def _seam_rows(boxes, scores, labels):
+    return np.concatenate([np.asarray(boxes, np.float64), np.asarray(scores, np.float64)[:, None], np.asarray(labels, np.float64)[:, None]], 1)
+
+
+def test_cross_seam_fast_path_falls_back_exactly():
+    """The sparse parallel form of the stage (nms_grid.cu) is exact on its own terms and must hand over to the general
+    pipeline when it does not apply: (a) a dependency chain longer than its round limit - a row of boxes, each suppressed by
+    its left neighbour alone, scores falling to the right, so the greedy result alternates keep / drop along 400 boxes;
+    (b) a pile of near-identical boxes - far more suppressors per box than the per-box list holds; (c) both mixed with a
+    sparse random field in two classes.  All straddle the seam at x = 192 or y = 192 (tile 256, edge 32 -> zone 192)."""
+    from yolo3_b200 import post_engine
+    H, W, tile, edge = 800, 9000, (256, 256), 32
+    eng = post_engine()
+    # (a) chain: 40-px-wide boxes stepping 10 px (IoU 0.6 with the neighbour, 0.33 with the next-but-one - above 0.3 too,
+    #     still a chain of decisions), all crossing y = 192
+    n = 400
+    x0 = 100 + 10 * np.arange(n)
+    chain = _seam_rows(np.stack([x0, np.full(n, 170), x0 + 40, np.full(n, 215)], 1), 0.9 - 0.001 * np.arange(n), np.zeros(n))
+    # (b) pile: 120 boxes jittered by one pixel around the seam crossing (192, 384)
+    rng = np.random.default_rng(1)
+    j = rng.integers(0, 2, (120, 4))
+    pile = _seam_rows(np.array([150, 340, 230, 420]) + j, pp.make_tie_free_scores(120, rng), np.ones(120))
+    # (c) sparse random field
+    m = 3000
+    cx, cy = rng.uniform(0, W, m), rng.uniform(0, H, m)
+    w, h = rng.uniform(10, 90, m), rng.uniform(10, 90, m)
+    field = _seam_rows(np.stack([np.clip(np.round(cx - w / 2), 0, W - 1), np.clip(np.round(cy - h / 2), 0, H - 1),
+                                 np.clip(np.round(cx + w / 2), 0, W - 1), np.clip(np.round(cy + h / 2), 0, H - 1)], 1),
+                       pp.make_tie_free_scores(m, rng), rng.integers(0, 2, m))
+    for name, pred in (("chain", chain), ("pile", pile), ("field", field), ("mixed", np.concatenate([field, chain, pile]))):
+        want = tl.cross_seam_nms(pred, (H, W), tile, edge, 0.3)
+        got = eng.cross_seam_nms(pred, (H, W), tile, edge, 0.3, number_classes=2)
+        assert np.array_equal(got, want), name
+        assert want.shape[0] < pred.shape[0], name
