@@ -298,6 +298,40 @@ def aux_k4_edge96(local, args, peaks, img, w):
             "heads_rel_err_vs_fp32_oracle_2_tiles": herr, "heads_within_2e-2": bool(max(herr) <= 2e-2)}
 
 
+def aux_cross_seam_sparse(local, args, peaks, img, w):
+    """The optional cross-seam stage (north_star; not in the reference) in the regime it is made for: detections of bounded
+    size spread over the image (100 k boxes of 20-200 px on the 20000^2 grid of 512^2 tiles, edge 64 -> ~49 k seam candidates).
+    The bench's own random-weight boxes are heavy-tailed (a fifth of them larger than 1024 px), which sends the stage down its
+    general (serial-chunk) route - that number is in aux_cross_seam of the multi-GPU lines."""
+    import torch
+    from oracle import tiling_np as tl, nms_c
+    from yolo3_b200 import post_engine
+    pe = post_engine(local)
+    side = 20000
+    rng = np.random.default_rng(5)
+
+    def boxes(n, ext):
+        cx, cy = rng.uniform(0, ext, n), rng.uniform(0, ext, n)
+        bw, bh = rng.uniform(20, 200, n), rng.uniform(20, 200, n)
+        return np.stack([np.clip(np.round(cx - bw / 2), 0, ext - 1), np.clip(np.round(cy - bh / 2), 0, ext - 1),
+                         np.clip(np.round(cx + bw / 2), 0, ext - 1), np.clip(np.round(cy + bh / 2), 0, ext - 1),
+                         rng.permutation(n).astype(np.float64) / n * 0.9 + 0.1, np.zeros(n)], 1)
+    rows = torch.from_numpy(boxes(100_000, side)).to(torch.device("cuda", local))
+    pe.cross_seam_nms(rows, (side, side), TILE, 64, 0.3, number_classes=1)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        out = pe.cross_seam_nms(rows, (side, side), TILE, 64, 0.3, number_classes=1)
+        torch.cuda.synchronize()
+        ts.append(1e3 * (time.perf_counter() - t0))
+    small = boxes(20_000, 8000)
+    want = tl.cross_seam_nms(small, (8000, 8000), TILE, 64, 0.3)
+    got = pe.cross_seam_nms(small, (8000, 8000), TILE, 64, 0.3, number_classes=1)
+    return {"rows_in": 100_000, "rows_out": int(out.shape[0]), "ms_stage_min": float(np.min(ts)), "ms_stage_median": float(np.median(ts)),
+            "equals_oracle_stage_on_20k_sample": bool(np.array_equal(got, want))}
+
+
 def aux_k5(local, rank, world, args, peaks, barrier, dist, dev):
     """BASELINE configs[4]: 608x608x3, NC=80, batch 256 = 32 images per GPU, plain data parallel (no exchange): every rank
     runs forward + decode + filter + NMS on its 32 images; images/s = all ranks' images / max-over-ranks time."""
@@ -539,7 +573,8 @@ def main():
         if world == 1:
             del eng
             torch.cuda.empty_cache()
-            for name, fn in (("aux_nms_k3", aux_k3), ("aux_k2_416_b64_nc80", aux_k2), ("aux_k1_416_b1_nc80", aux_k1), ("aux_k4_edge96", aux_k4_edge96)):
+            for name, fn in (("aux_nms_k3", aux_k3), ("aux_k2_416_b64_nc80", aux_k2), ("aux_k1_416_b1_nc80", aux_k1), ("aux_k4_edge96", aux_k4_edge96),
+                             ("aux_cross_seam_sparse", aux_cross_seam_sparse)):
                 try:
                     line[name] = fn(local, args, peaks, img, w)
                 except Exception as ex:                      # auxiliary only - never fail the headline line

@@ -8,9 +8,12 @@
 // Decisions are final and only ever use final decisions, so the result is the serial one regardless of scheduling.  The
 // number of rounds is the longest dominator chain - a few tens for boxes that were already NMS-ed inside their tiles.
 //
-//   k_grid_bounds   largest box side -> cell size G (two overlapping boxes have centres in the same or adjacent cells)
-//   k_grid_count / k_grid_scan / k_grid_fill     counting sort of the candidates by cell
-//   k_grid_dominators   every candidate walks the 3x3 cells around it and records its dominators (fixed capacity per box)
+//   k_grid_bounds   histogram of the box sides -> cell size G = the power of two that holds 95 % of the boxes (two
+//                   overlapping boxes no larger than a cell have centres in the same or adjacent cells); the few larger
+//                   boxes ("big": clamped giants, outliers) go to a separate list instead of blowing the cell size up
+//   k_grid_count / k_grid_scan / k_grid_fill     counting sort of the normal candidates by cell, big ones appended behind
+//   k_grid_dominators   a normal candidate walks the 3x3 cells around it plus the big list, a big one walks everything;
+//                   each records its dominators (fixed capacity per box)
 //   k_grid_round    one round of decisions; the host reads the number of undecided boxes every few rounds
 // A box with more dominators than the capacity, or a chain longer than the round limit, makes the caller fall back to
 // the general pipeline (PostProc::run) - exactness never depends on the fast path.
@@ -18,52 +21,73 @@
 #include "tiles.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 
 namespace y3 {
 
 static constexpr int GRID_DOM_CAP = 32;       // dominators recorded per box
 static constexpr int GRID_MAX_ROUNDS = 96;
 
+static constexpr int GRID_MAX_BIG = 4096;     // boxes larger than a cell that the fast path accepts
+
 struct GridCtrl {
     int n_cand;           // candidates
     int cell;             // cell size in pixels
     int gx, gy;           // grid dimensions
-    int overflow;         // a box had more than GRID_DOM_CAP dominators
+    int overflow;         // a box had more than GRID_DOM_CAP dominators, or there are too many big boxes
     int undecided;        // boxes still undecided after the last round
-    float max_side;
-    int pad_;
+    int n_big;            // candidates with a side larger than the cell
+    int n_norm;           // the others (cell-sorted part of `members`)
+    int hist[32];         // candidates by ceil(log2(largest side))
 };
 
 __device__ __forceinline__ bool higher_priority(float sj, int rj, float si, int ri) { return sj > si || (sj == si && rj < ri); }
 
-__global__ void __launch_bounds__(256)
-k_grid_bounds(const float4* __restrict__ box, const uint8_t* __restrict__ cand, int64_t n, GridCtrl* __restrict__ G) {
-    float m = 0.f;
-    int c = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        if (cand[i]) {
-            const float4 b = box[i];
-            m = fmaxf(m, fmaxf(b.z - b.x, b.w - b.y));
-            ++c;
-        }
-    for (int o = 16; o; o >>= 1) { m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o)); c += __shfl_xor_sync(0xffffffffu, c, o); }
-    if ((threadIdx.x & 31) == 0) {
-        if (c) atomicAdd(&G->n_cand, c);
-        atomicMax(reinterpret_cast<int*>(&G->max_side), __float_as_int(m));       // m >= 0: int order == float order
-    }
+__device__ __forceinline__ float box_side(const float4 b) { return fmaxf(b.z - b.x, b.w - b.y); }
+__device__ __forceinline__ int side_bucket(float side) {           // smallest k with side <= 2^k (0 for side <= 1, NaN -> 31)
+    if (!(side <= 1.0e9f)) return 31;
+    int k = 0;
+    while (k < 31 && (float)(1u << k) < side) ++k;
+    return k;
 }
 
-// one thread: cell size and grid dimensions (bounded so that the cell table stays small)
+__global__ void __launch_bounds__(256)
+k_grid_bounds(const float4* __restrict__ box, const uint8_t* __restrict__ cand, int64_t n, GridCtrl* __restrict__ G) {
+    __shared__ int s_hist[32];
+    if (threadIdx.x < 32) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (cand[i]) atomicAdd(&s_hist[side_bucket(box_side(box[i]))], 1);
+    __syncthreads();
+    if (threadIdx.x < 32 && s_hist[threadIdx.x]) atomicAdd(&G->hist[threadIdx.x], s_hist[threadIdx.x]);
+}
+
+// one thread: cell size = the power of two that holds 95 % of the candidates (at least 64 px, and large enough that the
+// cell table stays within max_cells_side^2)
 __global__ void k_grid_setup(GridCtrl* __restrict__ G, long long img_w, long long img_h, int max_cells_side) {
-    float side = G->max_side;
-    if (!(side >= 1.f)) side = 1.f;                                 // NaN / degenerate: any positive cell size works
-    long long cell = (long long)ceilf(side) + 1;
+    long long total = 0;
+    for (int k = 0; k < 32; ++k) total += G->hist[k];
+    G->n_cand = (int)total;
+    long long acc = 0;
+    int kb = 6;
+    for (int k = 0; k < 31; ++k) {
+        acc += G->hist[k];
+        if (k >= 6 && acc * 100 >= total * 95) { kb = k; break; }
+        kb = k + 1;
+    }
     const long long need = (max(img_w, img_h) + max_cells_side - 1) / max_cells_side;
-    cell = max(cell, max(need, 16ll));
+    kb = min(kb, 10);                                               // cells of at most 1024 px (unless the table bound asks for more):
+    long long cell = (1ll << kb) + 1;                               // whatever is larger is a "big" box
+    cell = max(cell, need);
+    long long big = 0;
+    for (int k = 0; k < 32; ++k) if ((1ll << k) > cell - 1) big += G->hist[k];     // upper bound of the big list
+    if (big > GRID_MAX_BIG) G->overflow = 1;                        // heavy-tailed sizes: not a sparse problem
     G->cell = (int)min(cell, 1ll << 30);
     G->gx = (int)((img_w + G->cell - 1) / G->cell) + 1;
     G->gy = (int)((img_h + G->cell - 1) / G->cell) + 1;
 }
+
+__device__ __forceinline__ bool is_big(const float4 b, const GridCtrl& G) { return !(box_side(b) <= (float)(G.cell - 1)); }
 
 __device__ __forceinline__ int cell_of(const float4 b, const GridCtrl& G) {
     // centre of the box, clamped into the grid (coordinates are clamped pixel corners, NaN goes to cell 0)
@@ -75,15 +99,19 @@ __device__ __forceinline__ int cell_of(const float4 b, const GridCtrl& G) {
 }
 
 __global__ void __launch_bounds__(256)
-k_grid_count(const float4* __restrict__ box, const uint8_t* __restrict__ cand, int64_t n, const GridCtrl* __restrict__ Gp,
+k_grid_count(const float4* __restrict__ box, const uint8_t* __restrict__ cand, int64_t n, GridCtrl* __restrict__ Gp,
              int* __restrict__ cell_cnt, int* __restrict__ slot) {
     const GridCtrl G = *Gp;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        if (cand[i]) slot[i] = atomicAdd(&cell_cnt[cell_of(box[i], G)], 1);
+        if (cand[i]) {
+            const float4 b = box[i];
+            if (is_big(b, G)) slot[i] = -1 - atomicAdd(&Gp->n_big, 1);            // negative: index in the big list
+            else slot[i] = atomicAdd(&cell_cnt[cell_of(b, G)], 1);
+        }
 }
 
 __global__ void __launch_bounds__(1024)
-k_grid_scan(int* __restrict__ cell_cnt, int* __restrict__ cell_off, const GridCtrl* __restrict__ Gp) {
+k_grid_scan(int* __restrict__ cell_cnt, int* __restrict__ cell_off, GridCtrl* __restrict__ Gp) {
     __shared__ long long s_part[1024];
     const int n = Gp->gx * Gp->gy;
     const int per = (n + 1023) / 1024;
@@ -101,7 +129,11 @@ k_grid_scan(int* __restrict__ cell_cnt, int* __restrict__ cell_off, const GridCt
     long long run = s_part[threadIdx.x] - sum;
     for (int i = 0; i < per; ++i)
         if (b0 + i < n) { cell_off[b0 + i] = (int)run; run += cell_cnt[b0 + i]; }
-    if (threadIdx.x == 1023) cell_off[n] = (int)s_part[1023];
+    if (threadIdx.x == 1023) {
+        cell_off[n] = (int)s_part[1023];
+        Gp->n_norm = (int)s_part[1023];
+        if (Gp->n_big > GRID_MAX_BIG) Gp->overflow = 1;
+    }
 }
 
 // members[cell_off[cell] + slot] = row;  state: 0 undecided, 1 kept, 2 dead
@@ -111,7 +143,10 @@ k_grid_fill(const float4* __restrict__ box, const uint8_t* __restrict__ cand, in
     const GridCtrl G = *Gp;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         state[i] = 0;
-        if (cand[i]) members[cell_off[cell_of(box[i], G)] + slot[i]] = (int)i;
+        if (!cand[i]) continue;
+        const int sl = slot[i];
+        if (sl < 0) members[G.n_norm + (-1 - sl)] = (int)i;                 // big boxes behind the cell-sorted ones
+        else members[cell_off[cell_of(box[i], G)] + sl] = (int)i;
     }
 }
 
@@ -121,20 +156,15 @@ k_grid_dominators(const float4* __restrict__ box, const float* __restrict__ scor
                   int* __restrict__ n_dom) {
     const GridCtrl G = *Gp;
     const int m = G.n_cand;
+    if (G.overflow) return;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < m; p += gridDim.x * blockDim.x) {
         const int i = members[p];
         const float4 bi = box[i];
         const float ai = box_area_exact(bi);
         const float si = score[i];
         const int li = label[i];
-        const int c = cell_of(bi, G);
-        const int cy = c / G.gx, cx = c - cy * G.gx;
         int nd = 0;
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int y = cy + dy;
-            if (y < 0 || y >= G.gy) continue;
-            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, G.gx - 1);
-            const int q0 = cell_off[y * G.gx + x0], q1 = cell_off[y * G.gx + x1 + 1];     // the three cells of a row are contiguous
+        auto visit = [&](int q0, int q1) {
             for (int q = q0; q < q1; ++q) {
                 const int j = members[q];
                 if (j == i || label[j] != li) continue;
@@ -147,6 +177,19 @@ k_grid_dominators(const float4* __restrict__ box, const float* __restrict__ scor
                     ++nd;
                 }
             }
+        };
+        if (p >= G.n_norm) {
+            visit(0, m);                                          // a big box: everything
+        } else {
+            const int c = cell_of(bi, G);
+            const int cy = c / G.gx, cx = c - cy * G.gx;
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int y = cy + dy;
+                if (y < 0 || y >= G.gy) continue;
+                const int x0 = max(cx - 1, 0), x1 = min(cx + 1, G.gx - 1);
+                visit(cell_off[y * G.gx + x0], cell_off[y * G.gx + x1 + 1]);     // the three cells of a row are contiguous
+            }
+            visit(G.n_norm, m);                                   // plus the big boxes
         }
         n_dom[p] = nd;
         if (nd > GRID_DOM_CAP) Gp->overflow = 1;
@@ -180,6 +223,12 @@ k_grid_round(const int* __restrict__ members, const int* __restrict__ dom, const
 __global__ void k_grid_reset_undecided(GridCtrl* __restrict__ G) { G->undecided = 0; }
 
 __global__ void __launch_bounds__(256)
+k_grid_keepmask_all(int64_t n, uint8_t* __restrict__ keepm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keepm[i] = 1;
+}
+
+__global__ void __launch_bounds__(256)
 k_grid_keepmask(const uint8_t* __restrict__ cand, const uint8_t* __restrict__ state, int64_t n, uint8_t* __restrict__ keepm) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) keepm[i] = (!cand[i] || state[i] == 1) ? 1 : 0;
@@ -205,7 +254,17 @@ bool Tiler::cross_seam_grid(const float4* box, const float* score, const int32_t
     Y3_LAUNCHED(ctx);
     k_grid_setup<<<1, 1, 0, st>>>(G, (long long)S.img_w, (long long)S.img_h, max_side_cells);
     Y3_LAUNCHED(ctx);
-    Y3_CUDA(cudaMemsetAsync(cell_cnt, 0, (size_t)(max_side_cells + 2) * (max_side_cells + 2) * 4, st));
+    GridCtrl* hG = grid_host.as<GridCtrl>();
+    Y3_CUDA(cudaMemcpyAsync(hG, G, sizeof(GridCtrl), cudaMemcpyDeviceToHost, st));
+    Y3_CUDA(cudaStreamSynchronize(st));
+    static const bool dbg = getenv("Y3_DEBUG_TIMING") != nullptr;
+    if (hG->overflow || hG->n_cand == 0) {
+        if (dbg) fprintf(stderr, "y3: cross-seam grid: %d candidates, cell %d px: too many oversized boxes for the sparse path\n", hG->n_cand, hG->cell);
+        if (hG->n_cand == 0) { k_grid_keepmask_all<<<ceil_div(n, 256), 256, 0, st>>>(n, keepm); Y3_LAUNCHED(ctx); return true; }
+        return false;
+    }
+    const size_t n_cells = (size_t)hG->gx * hG->gy;
+    Y3_CUDA(cudaMemsetAsync(cell_cnt, 0, n_cells * 4, st));
     k_grid_count<<<blocks, 256, 0, st>>>(box, cand, n, G, cell_cnt, grid_slot.as<int>());
     Y3_LAUNCHED(ctx);
     k_grid_scan<<<1, 1024, 0, st>>>(cell_cnt, cell_off, G);
@@ -216,9 +275,10 @@ bool Tiler::cross_seam_grid(const float4* box, const float* score, const int32_t
     k_grid_dominators<<<dblocks, 128, 0, st>>>(box, score, label, G, cell_off, grid_members.as<int>(), iou_thr, grid_dom.as<int>(),
                                                grid_ndom.as<int>());
     Y3_LAUNCHED(ctx);
-    GridCtrl* hG = grid_host.as<GridCtrl>();
     bool done = false;
+    int rounds_run = 0;
     for (int round = 0; round < GRID_MAX_ROUNDS && !done; round += 4) {
+        rounds_run = round + 4;
         for (int r = 0; r < 4; ++r) {
             if (r == 3) { k_grid_reset_undecided<<<1, 1, 0, st>>>(G); Y3_LAUNCHED(ctx); }
             k_grid_round<<<blocks, 256, 0, st>>>(grid_members.as<int>(), grid_dom.as<int>(), grid_ndom.as<int>(), G,
@@ -227,6 +287,12 @@ bool Tiler::cross_seam_grid(const float4* box, const float* score, const int32_t
         }
         Y3_CUDA(cudaMemcpyAsync(hG, G, sizeof(GridCtrl), cudaMemcpyDeviceToHost, st));
         Y3_CUDA(cudaStreamSynchronize(st));
+        if (dbg) {
+            fprintf(stderr, "y3: cross-seam grid: %d candidates (%d big), cell %d px, after %d rounds %d undecided, overflow %d; sides by log2:", hG->n_cand,
+                    hG->n_big, hG->cell, rounds_run, hG->undecided, hG->overflow);
+            for (int k = 0; k < 32; ++k) if (hG->hist[k]) fprintf(stderr, " 2^%d:%d", k, hG->hist[k]);
+            fprintf(stderr, "\n");
+        }
         if (hG->overflow) return false;
         done = hG->undecided == 0;
     }
