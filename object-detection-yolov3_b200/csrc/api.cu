@@ -211,7 +211,7 @@ y3_status y3_forward_heads(y3_handle h, const float* in, y3_mem in_mem, int32_t 
         const int hw = net->gh[s] * net->gw[s];
         const size_t bytes = (size_t)batch * net->det_c * hw * 4;
         float* dst = out_mem == Y3_MEM_DEVICE ? outs[s] : (h->stage_out.reserve(bytes), h->stage_out.as<float>());
-        heads_to_nchw(h, net->head[s], dst, batch, hw, net->det_c, net->head_pitch);
+        heads_to_nchw(h, net->head[s], dst, batch, hw, net->det_c, net->head_pitch, net->na, net->nc);
         if (out_mem != Y3_MEM_DEVICE) {
             from_device(h, outs[s], out_mem, dst, bytes);
             Y3_CUDA(cudaStreamSynchronize(h->stream));

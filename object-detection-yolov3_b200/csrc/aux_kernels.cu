@@ -120,16 +120,26 @@ __device__ __forceinline__ __nv_bfloat16 to_operand16(float v, bool f16) {
 }
 
 __global__ void k_pack_conv_w(const float* __restrict__ k /*[taps,Cin,Cout]*/, __nv_bfloat16* __restrict__ out,
-                              int taps, int cin, int cout, int cout_pad, int f16) {
+                              int taps, int cin, int cout, int cout_pad, int f16, int det_na, int det_nc) {
     const long long n = (long long)cout_pad * taps * cin;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = to_operand16(0.f, f16 != 0);
+    // second sweep: rows land at their stored position - the identity (same thread, same element) except for detection
+    // layers, which run as ONE block so that this barrier orders the zero fill before the permuted writes
+    __syncthreads();
+    const long long m = (long long)cout * taps * cin;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
         const int ci = (int)(i % cin);
         const long long r = i / cin;
         const int tap = (int)(r % taps);
-        const int co = (int)(r / taps);
-        const float v = co < cout ? k[((long long)tap * cin + ci) * cout + co] : 0.f;
-        out[i] = to_operand16(v, f16 != 0);
+        const int co = (int)(r / taps);                                       // reference output channel
+        const int row = det_na > 0 ? head_pos(det_na, det_nc, co) : co;       // stored row
+        out[((long long)row * taps + tap) * cin + ci] = to_operand16(k[((long long)tap * cin + ci) * cout + co], f16 != 0);
     }
+}
+__global__ void k_permute_det_bias(const float* __restrict__ ref_bias, float* __restrict__ out, int na, int nc) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < na * (5 + nc)) out[head_pos(na, nc, c)] = ref_bias[c];
 }
 __global__ void k_pack_convt_w(const float* __restrict__ k /*[4,Cout,Cin]*/, __nv_bfloat16* __restrict__ out, long long n, int f16) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -182,9 +192,16 @@ void compose_up(y3_context* ctx, const float* wy, const float* kt, const float* 
     Y3_LAUNCHED(ctx);
 }
 
-void pack_conv_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, int taps, int cin, int cout, int cout_pad, bool f16) {
+void pack_conv_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, int taps, int cin, int cout, int cout_pad, bool f16, int det_na,
+                      int det_nc) {
     const long long n = (long long)cout_pad * taps * cin;
-    k_pack_conv_w<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, ctx->stream>>>(k, out, taps, cin, cout, cout_pad, f16 ? 1 : 0);
+    // one block: the zero fill of the padded rows and the (possibly permuted) row writes must not race
+    if (det_na > 0) k_pack_conv_w<<<1, 1024, 0, ctx->stream>>>(k, out, taps, cin, cout, cout_pad, f16 ? 1 : 0, det_na, det_nc);
+    else k_pack_conv_w<<<(int)std::min<long long>((n + 255) / 256, 4096), 256, 0, ctx->stream>>>(k, out, taps, cin, cout, cout_pad, f16 ? 1 : 0, 0, 0);
+    Y3_LAUNCHED(ctx);
+}
+void permute_det_bias(y3_context* ctx, const float* ref_bias, float* out, int na, int nc) {
+    k_permute_det_bias<<<(na * (5 + nc) + 127) / 128, 128, 0, ctx->stream>>>(ref_bias, out, na, nc);
     Y3_LAUNCHED(ctx);
 }
 void pack_convt_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, long long n, bool f16) {
@@ -197,19 +214,19 @@ void bn_fold(y3_context* ctx, const float* g, const float* b, const float* m, co
 }
 
 // ------------------------------------------------------------------------------------------ heads
-__global__ void k_heads_to_nchw(const float* __restrict__ in, float* __restrict__ out, int B, int HW, int C, int pitch) {
+__global__ void k_heads_to_nchw(const float* __restrict__ in, float* __restrict__ out, int B, int HW, int C, int pitch, int na, int nc) {
     const long long n = (long long)B * C * HW;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int p = (int)(i % HW);
         const long long r = i / HW;
         const int c = (int)(r % C);
         const int b = (int)(r / C);
-        out[i] = in[((long long)b * HW + p) * pitch + c];
+        out[i] = in[((long long)b * HW + p) * pitch + head_pos(na, nc, c)];      // back to the reference's channel order
     }
 }
-void heads_to_nchw(y3_context* ctx, const float* in, float* out, int B, int HW, int C, int pitch) {
+void heads_to_nchw(y3_context* ctx, const float* in, float* out, int B, int HW, int C, int pitch, int na, int nc) {
     const long long n = (long long)B * C * HW;
-    k_heads_to_nchw<<<(int)std::min<long long>((n + 255) / 256, 8192), 256, 0, ctx->stream>>>(in, out, B, HW, C, pitch);
+    k_heads_to_nchw<<<(int)std::min<long long>((n + 255) / 256, 8192), 256, 0, ctx->stream>>>(in, out, B, HW, C, pitch, na, nc);
     Y3_LAUNCHED(ctx);
 }
 
@@ -246,8 +263,9 @@ k_decode(DecodeArgs D, float* __restrict__ out) {
         const int row = (int)(r / E);
         const int k = (int)(r - (long long)row * E);
         int s, cell, a;
-        const float* hp = head_row(D, b, row, &s, &cell, &a);
-        out[i] = (k >= 4) ? sigmoid_f(__ldg(hp + k)) : decode_corner(D, hp, s, cell, a, k);
+        const float* ho;
+        const float* hp = head_row(D, b, row, &s, &cell, &a, &ho);
+        out[i] = (k == 4) ? sigmoid_f(__ldg(ho)) : (k > 4) ? sigmoid_f(__ldg(hp + k - 1)) : decode_corner(D, hp, s, cell, a, k);
     }
 }
 void launch_decode(y3_context* ctx, const DecodeArgs& D, float* out) {

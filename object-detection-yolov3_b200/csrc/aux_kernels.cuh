@@ -20,8 +20,19 @@ struct DecodeArgs {
 //   cx = (sigmoid(tx) + j) * stride ; w = exp(tw) * anchor_w ; x0 = cx - w / 2 ; x1 = cx + w / 2
 __device__ __forceinline__ float sigmoid_f(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
-// pointer to the (5+NC) logits of output row `row` of image b, plus its grid cell / anchor / scale
-__device__ __forceinline__ const float* head_row(const DecodeArgs& D, int b, int row, int* s_out, int* cell_out, int* a_out) {
+// Stored channel order of one head cell (pitch floats): the A objectness logits first, then per anchor tx ty tw th and the
+// class logits:  [obj_0 .. obj_{A-1} | a=0: tx ty tw th cls_0 .. | a=1: ... ].  It is a permutation of the detection
+// layer's output channels (reference order a*(5+NC)+k), applied to the weight rows at load time, so the convolution writes
+// it for free - and the threshold pass, which looks at the objectness of every row first, finds the A logits of a cell in
+// ONE 32-byte sector instead of A different 128-byte lines (K2: 87 -> 29 MB of line traffic).
+__host__ __device__ __forceinline__ int head_pos(int na, int nc, int ref_channel) {
+    const int a = ref_channel / (5 + nc), k = ref_channel - a * (5 + nc);
+    return k == 4 ? a : na + a * (4 + nc) + (k < 4 ? k : k - 1);
+}
+// pointer to the box + class logits of output row `row` of image b (hp[0..3] = tx ty tw th, hp[4 + c] = class c), the
+// address of its objectness logit, and its grid cell / anchor / scale
+__device__ __forceinline__ const float* head_row(const DecodeArgs& D, int b, int row, int* s_out, int* cell_out, int* a_out,
+                                                 const float** obj_out) {
     int s = 0;
     if (row >= D.row_start[1]) s = 1;
     if (row >= D.row_start[2]) s = 2;
@@ -29,7 +40,9 @@ __device__ __forceinline__ const float* head_row(const DecodeArgs& D, int b, int
     const int cell = lr / D.na;
     const int a = lr - cell * D.na;
     *s_out = s; *cell_out = cell; *a_out = a;
-    return D.head[s] + ((long long)b * D.gh[s] * D.gw[s] + cell) * D.pitch + a * (5 + D.nc);
+    const float* base = D.head[s] + ((long long)b * D.gh[s] * D.gw[s] + cell) * D.pitch;
+    *obj_out = base + a;
+    return base + D.na + a * (4 + D.nc);
 }
 // k in 0..3 : x0, y0, x1, y1
 __device__ __forceinline__ float decode_corner(const DecodeArgs& D, const float* hp, int s, int cell, int a, int k) {
@@ -68,12 +81,15 @@ void launch_stem(y3_context* ctx, const float* in, __nv_bfloat16* out, const flo
 bool launch_stem_tc(y3_context* ctx, const float* in, __nv_bfloat16* out, const float* w, const float* bias, const float* scale,
                     const float* shift, int B, int H, int W, int cin);
 // f16: pack as fp16 instead of bf16 (layers whose input tensor is fp16 - the tail after the first upsample)
-void pack_conv_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, int taps, int cin, int cout, int cout_pad, bool f16 = false);
+// det_na > 0: a detection layer - output rows stored in head_pos() order
+void pack_conv_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, int taps, int cin, int cout, int cout_pad, bool f16 = false,
+                      int det_na = 0, int det_nc = 0);
+void permute_det_bias(y3_context* ctx, const float* ref_bias, float* out, int na, int nc);
 void pack_convt_weight(y3_context* ctx, const float* k, __nv_bfloat16* out, long long n, bool f16 = false);
 void compose_up(y3_context* ctx, const float* wy, const float* kt, const float* by, const float* bt, int c_up, int c_x, int c_r,
                 int cout, __nv_bfloat16* w_out, float* b_out, bool x_f16 = false, bool r_f16 = false);
 void bn_fold(y3_context* ctx, const float* g, const float* b, const float* m, const float* v, float* s, float* t, int c);
-void heads_to_nchw(y3_context* ctx, const float* in, float* out, int B, int HW, int C, int pitch);
+void heads_to_nchw(y3_context* ctx, const float* in, float* out, int B, int HW, int C, int pitch, int na, int nc);
 void slice_to_nchw(y3_context* ctx, const __nv_bfloat16* in, float* out, int B, int H, int W, int C, int pitch, int coff, bool f16 = false);
 void launch_decode(y3_context* ctx, const DecodeArgs& D, float* out);
 

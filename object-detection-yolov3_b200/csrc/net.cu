@@ -602,7 +602,13 @@ void Net::load(int n, const char* const* names, DLManagedTensor* const* tensors_
             op->have |= (4u << slot);
         } else if (var == "bias") {
             Y3_CHECK(numel == op->cout, Y3_ERR_INVALID, "weight '%s': expected %d values, got %lld", names[i], op->cout, (long long)numel);
-            Y3_CUDA(cudaMemcpyAsync(op->bias.p, src, (size_t)numel * 4, kind, st));
+            if (op->kind == Op::DET) {                          // stored channel order of the heads (aux_kernels.cuh head_pos)
+                stage.reserve((size_t)numel * 4);
+                Y3_CUDA(cudaMemcpyAsync(stage.p, src, (size_t)numel * 4, kind, st));
+                permute_det_bias(ctx, stage.as<float>(), op->bias.as<float>(), na, nc);
+            } else {
+                Y3_CUDA(cudaMemcpyAsync(op->bias.p, src, (size_t)numel * 4, kind, st));
+            }
             op->have |= 2u;
         } else if (var == "kernel") {
             const int64_t expect = (int64_t)taps * op->cin * op->cout;
@@ -615,7 +621,8 @@ void Net::load(int n, const char* const* names, DLManagedTensor* const* tensors_
                 Y3_CUDA(cudaMemcpyAsync(stage.p, src, (size_t)numel * 4, kind, st));
                 const bool w_f16 = this->tensors[op->in.t].f16;       // weights in the format of the tensor they multiply
                 if (op->kind == Op::CONVT) pack_convt_weight(ctx, stage.as<float>(), op->w.as<__nv_bfloat16>(), numel, w_f16);
-                else pack_conv_weight(ctx, stage.as<float>(), op->w.as<__nv_bfloat16>(), taps, op->cin, op->cout, op->cout_pad, w_f16);
+                else pack_conv_weight(ctx, stage.as<float>(), op->w.as<__nv_bfloat16>(), taps, op->cin, op->cout, op->cout_pad, w_f16,
+                                      op->kind == Op::DET ? na : 0, nc);
             }
             op->have |= 1u;
         } else {

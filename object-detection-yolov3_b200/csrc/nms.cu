@@ -102,8 +102,9 @@ k_candidates(CandSource src, KeyLayout kl, int64_t total, float logit_floor, Can
             if (src.from_heads) {
                 // fused decode: sigmoid of the objectness / class logits straight from the head (model.py:184-185)
                 int sc, cell, a;
-                const float* hp = head_row(src.dec, (int)img, (int)row, &sc, &cell, &a);
-                const float lo = __ldg(hp + 4), lc = __ldg(hp + 5 + c);
+                const float* ho;
+                const float* hp = head_row(src.dec, (int)img, (int)row, &sc, &cell, &a, &ho);
+                const float lo = __ldg(ho), lc = __ldg(hp + 4 + c);
                 // exact conservative pre-filter: score^2 = obj*cls <= min(obj, cls); a logit below
                 // logit(thr^2) - margin cannot reach the threshold, so both sigmoids are skipped
                 if (lo >= logit_floor && lc >= logit_floor) {
@@ -174,10 +175,11 @@ k_candidates_heads1(CandSource src, KeyLayout kl, float logit_floor, CandOut O) 
             img = grow / rpi;
             row = grow - img * rpi;
             int sc, cell, a;
-            const float* hp = head_row(src.dec, (int)img, (int)row, &sc, &cell, &a);
-            const float lo = __ldg(hp + 4);
+            const float* ho;
+            const float* hp = head_row(src.dec, (int)img, (int)row, &sc, &cell, &a, &ho);
+            const float lo = __ldg(ho);
             if (lo >= logit_floor) {
-                const float lc = __ldg(hp + 5);
+                const float lc = __ldg(hp + 4);
                 if (lc >= logit_floor) {
                     s = __fsqrt_rn(__fmul_rn(sigmoid_f(lc), sigmoid_f(lo)));
                     pass = (s >= thr);
@@ -205,8 +207,9 @@ k_live_rows(CandSource src, float logit_floor, uint32_t* __restrict__ live, unsi
         if (grow < rows_total) {
             const uint32_t img = grow / rpi;
             int sc, cell, a;
-            const float* hp = head_row(src.dec, (int)img, (int)(grow - img * rpi), &sc, &cell, &a);
-            alive = __ldg(hp + 4) >= logit_floor;
+            const float* ho;
+            head_row(src.dec, (int)img, (int)(grow - img * rpi), &sc, &cell, &a, &ho);
+            alive = __ldg(ho) >= logit_floor;
         }
         const unsigned m = __ballot_sync(0xffffffffu, alive);
         if (m) {
@@ -236,8 +239,9 @@ k_candidates_rows(CandSource src, KeyLayout kl, float logit_floor, const uint32_
         const uint32_t grow = live[li];
         const uint32_t img = grow / rpi, row = grow - img * rpi;
         int sc, cell, a;
-        const float* hp = head_row(src.dec, (int)img, (int)row, &sc, &cell, &a);
-        const float o = sigmoid_f(__ldg(hp + 4));
+        const float* ho;
+        const float* hp = head_row(src.dec, (int)img, (int)row, &sc, &cell, &a, &ho);
+        const float o = sigmoid_f(__ldg(ho));
         bool size_known = false, size_ok = true;
         float4 cbox = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int c00 = 0; c00 < nc; c00 += 32 * ROW_IT) {
@@ -245,7 +249,7 @@ k_candidates_rows(CandSource src, KeyLayout kl, float logit_floor, const uint32_
 #pragma unroll
             for (int it = 0; it < ROW_IT; ++it) {
                 const int c = c00 + it * 32 + lane;
-                lc[it] = (c < nc) ? __ldg(hp + 5 + c) : -INFINITY;
+                lc[it] = (c < nc) ? __ldg(hp + 4 + c) : -INFINITY;
             }
             float s[ROW_IT];
             unsigned pm[ROW_IT];
@@ -305,7 +309,8 @@ k_gather_sorted(CandSource src, const uint32_t* __restrict__ vals, int64_t n, fl
         const int64_t grow = vals[p];
         const int64_t img = grow / src.rows_per_image;
         int sc, cell, a;
-        const float* hp = head_row(src.dec, (int)img, (int)(grow - img * src.rows_per_image), &sc, &cell, &a);
+        const float* ho;
+        const float* hp = head_row(src.dec, (int)img, (int)(grow - img * src.rows_per_image), &sc, &cell, &a, &ho);
         bx = decode_box(src.dec, hp, sc, cell, a);
     } else {
         const float* b = src.box + (int64_t)vals[p] * src.box_stride;

@@ -137,7 +137,8 @@ __device__ __forceinline__ int gather_alive(const uint8_t* __restrict__ supp, in
 __device__ __forceinline__ float4 cand_box(const CandSource& src, int64_t img, int64_t row) {
     if (src.from_heads) {
         int sc, cell, a;
-        const float* hp = head_row(src.dec, (int)img, (int)row, &sc, &cell, &a);
+        const float* ho;
+        const float* hp = head_row(src.dec, (int)img, (int)row, &sc, &cell, &a, &ho);
         return decode_box(src.dec, hp, sc, cell, a);
     }
     const float* b = src.box + (img * src.rows_per_image + row) * src.box_stride;
