@@ -76,10 +76,12 @@ __device__ __forceinline__ int size_class(int c) {
     return c > 64 ? 8 : c > 32 ? 9 : 10;
 }
 
-__global__ void __launch_bounds__(1024)
-k2_scan(const int* __restrict__ seg_cnt, int nseg, int* __restrict__ seg_off, int* __restrict__ work_list,
-        int* __restrict__ kept_cnt, const unsigned long long* __restrict__ counter, long long cap, PostCtrl* __restrict__ C) {
-    pdl_chain_sync();
+// Exclusive scan of the per-segment counts + work list + control block, by ONE block of 1024 threads.
+//   s_table (optional, shared memory, nseg + 1 ints): the offsets also land there (k2_scan_bin: every block keeps its own copy)
+//   publish: this block writes the global results (segment offsets, work list, kept-count zeros, control block)
+__device__ __forceinline__ void seg_scan_block(const int* __restrict__ seg_cnt, int nseg, int* __restrict__ seg_off, int* __restrict__ work_list,
+                                               int* __restrict__ kept_cnt, const unsigned long long* __restrict__ counter, long long cap,
+                                               PostCtrl* __restrict__ C, int* s_table, bool publish, int* total_out, bool* overflow_out) {
     __shared__ int s_warp[33];
     __shared__ int s_cls[N_CLS], s_cls_off[N_CLS], s_max;
     const int tid = threadIdx.x;
@@ -110,13 +112,18 @@ k2_scan(const int* __restrict__ seg_cnt, int nseg, int* __restrict__ seg_off, in
         const int s = b0 + i;
         if (s >= nseg) break;
         const int c = seg_cnt[s];
-        seg_off[s] = overflow ? 0 : run;
+        if (s_table) s_table[s] = overflow ? 0 : run;
+        if (publish) {
+            seg_off[s] = overflow ? 0 : run;
+            if (overflow || c == 0 || c > SEG_MID_MAX) kept_cnt[s] = 0;          // nobody else will write it
+            else work_list[atomicAdd(&s_cls_off[size_class(c)], 1)] = s;
+        }
         run += c;
-        if (overflow || c == 0 || c > SEG_MID_MAX) kept_cnt[s] = 0;              // nobody else will write it
-        else work_list[atomicAdd(&s_cls_off[size_class(c)], 1)] = s;
     }
     __syncthreads();
-    if (tid == 0) {
+    *total_out = overflow ? 0 : total;
+    *overflow_out = overflow;
+    if (tid == 0 && publish) {
         int n_b = 0, n_cta = 0, n_all = 0;
         for (int k = 0; k < N_CLS; ++k) { n_all += s_cls[k]; if (k < N_CTA_CLS) n_cta += s_cls[k]; if (k < N_CTAB_CLS) n_b += s_cls[k]; }
         seg_off[nseg] = overflow ? 0 : total;
@@ -133,6 +140,37 @@ k2_scan(const int* __restrict__ seg_cnt, int nseg, int* __restrict__ seg_off, in
         C->n_kept_nms = 0;
         if (overflow) C->any_overflow = 1;
         C->sum_cand += (long long)n_cand;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k2_scan(const int* __restrict__ seg_cnt, int nseg, int* __restrict__ seg_off, int* __restrict__ work_list,
+        int* __restrict__ kept_cnt, const unsigned long long* __restrict__ counter, long long cap, PostCtrl* __restrict__ C) {
+    pdl_chain_sync();
+    int total;
+    bool overflow;
+    seg_scan_block(seg_cnt, nseg, seg_off, work_list, kept_cnt, counter, cap, C, nullptr, true, &total, &overflow);
+}
+
+// scan + bin in one launch (segment tables that fit shared memory): EVERY block scans the counts into its own
+// shared-memory table (a few microseconds of redundant L2 reads), block 0 publishes the global results for the kernels
+// that follow, then the blocks scatter their share of the keys and boxes.  Saves a launch and the single-CTA critical path.
+__global__ void __launch_bounds__(1024)
+k2_scan_bin(const int* __restrict__ seg_cnt, int nseg, int* __restrict__ seg_off, int* __restrict__ work_list,
+            int* __restrict__ kept_cnt, const unsigned long long* __restrict__ counter, long long cap, PostCtrl* __restrict__ C,
+            const uint64_t* __restrict__ keys, const uint32_t* __restrict__ slot, const float4* __restrict__ cbox, int seg_shift,
+            uint64_t* __restrict__ bkeys, float4* __restrict__ bbox) {
+    pdl_chain_sync();
+    extern __shared__ int s_table[];
+    int K;
+    bool overflow;
+    seg_scan_block(seg_cnt, nseg, seg_off, work_list, kept_cnt, counter, cap, C, s_table, blockIdx.x == 0, &K, &overflow);
+    __syncthreads();
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < K; p += gridDim.x * blockDim.x) {
+        const uint64_t key = keys[p];
+        const int dst = s_table[(int)(key >> seg_shift)] + (int)slot[p];
+        bkeys[dst] = key;
+        bbox[dst] = cbox[p];
     }
 }
 
@@ -467,6 +505,83 @@ k2_emit(const SegArgs A, const int* __restrict__ seg_off, const int* __restrict_
     }
 }
 
+// k2_out_scan + k2_emit in one launch: a block owns 8 consecutive segments (one per warp) and computes the output offset of
+// its first segment itself (a block-wide sum over the kept counts before it - a few loads per thread from L2); the block
+// that finishes last publishes the totals (and, on the tiled path, advances the row counter that every block has read
+// before).  Used when the segment table is small enough for the redundant sums to be cheap.
+__global__ void __launch_bounds__(256)
+k2_emit_fused(const SegArgs A, const int* __restrict__ seg_off, const int* __restrict__ kept_cnt, const float4* __restrict__ rbox,
+              const uint64_t* __restrict__ rkey, PostCtrl* __restrict__ C, EmitPlain P, double* __restrict__ preds, long long cap_rows) {
+    pdl_chain_sync();
+    __shared__ int s_red[8];
+    __shared__ int s_cnt[8];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int first = blockIdx.x * 8;
+    const long long base = A.tiled ? C->acc_rows : 0;           // read before this block takes its ticket
+    int part = 0;
+    for (int s = threadIdx.x; s < first; s += 256) part += kept_cnt[s];
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_red[wid] = part;
+    const int seg = first + wid;
+    const int n = seg < A.nseg ? kept_cnt[seg] : 0;
+    if (lane == 0) s_cnt[wid] = n;
+    __syncthreads();
+    int q0 = 0;
+    for (int w = 0; w < 8; ++w) q0 += s_red[w];
+    for (int w = 0; w < wid; ++w) q0 += s_cnt[w];
+    if (n > 0) {
+        const int s0 = seg_off[seg];
+        const int img = A.src.seg_image(seg), label = A.src.seg_label(seg);
+        TileGeo g{};
+        if (A.tiled) g = A.geo[img];
+        for (int t = lane; t < n; t += 32) {
+            const float4 bx = rbox[s0 + t];
+            const uint64_t key = rkey[s0 + t];
+            const float score = key_score(A.kl, key);
+            if (A.tiled) {
+                const long long q = base + q0 + t;
+                if (q < cap_rows) {
+                    int4 ib;
+                    stitch_box(bx, g, A.S, &ib);
+                    double* o = preds + q * 6;
+                    o[0] = ib.x; o[1] = ib.y; o[2] = ib.z; o[3] = ib.w;
+                    o[4] = (double)score;
+                    o[5] = (double)label;
+                }
+            } else {
+                const int q = q0 + t;
+                P.box[q] = bx;
+                P.score[q] = score;
+                P.label[q] = label;
+                P.img[q] = img;
+                P.src[q] = (int32_t)(key & A.kl.row_mask);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&C->emit_ticket, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {                                                // every other block has read acc_rows and written its rows
+        int tot = 0;
+        for (int s = threadIdx.x; s < A.nseg; s += 256) tot += kept_cnt[s];
+        for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (lane == 0) s_red[wid] = tot;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int total = 0;
+            for (int w = 0; w < 8; ++w) total += s_red[w];
+            C->n_kept = total;
+            C->sum_kept_nms += C->n_kept_nms;
+            if (A.tiled) { C->emit_base = C->acc_rows; C->acc_rows += total; }
+            C->emit_ticket = 0;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host
 bool PostProc::segmented_ok(const CandSource& src) { return src.rows_per_image <= SEG_MID_MAX; }
 
@@ -502,10 +617,17 @@ void PostProc::segmented_front(const CandSource& src, const KeyLayout& kl, int64
         launch_candidates(src, kl, cap, true);
         p.stop();
     }
-    launch_chained(ctx, k2_scan, 1, 1024, 0, st, seg_cnt.as<int>(), nseg, seg_off32.as<int>(), mid_list.as<int>(), kept_cnt.as<int>(),
-                   counters.as<unsigned long long>(), (long long)cap, ctrl.as<PostCtrl>());
-    launch_chained(ctx, k2_bin, ctx->sm_count * 4, 256, 0, st, keys[0].as<uint64_t>(), slot.as<uint32_t>(), cbox.as<float4>(), seg_off32.as<int>(),
-                   kl.seg_shift, ctrl.as<PostCtrl>(), bkeys.as<uint64_t>(), bbox.as<float4>());
+    static const bool fuse = getenv("Y3_NO_POST_FUSE") == nullptr;
+    if (fuse && nseg <= 12000) {
+        launch_chained(ctx, k2_scan_bin, ctx->sm_count, 1024, (size_t)(nseg + 1) * 4, st, seg_cnt.as<int>(), nseg, seg_off32.as<int>(),
+                       mid_list.as<int>(), kept_cnt.as<int>(), counters.as<unsigned long long>(), (long long)cap, ctrl.as<PostCtrl>(),
+                       keys[0].as<uint64_t>(), slot.as<uint32_t>(), cbox.as<float4>(), kl.seg_shift, bkeys.as<uint64_t>(), bbox.as<float4>());
+    } else {
+        launch_chained(ctx, k2_scan, 1, 1024, 0, st, seg_cnt.as<int>(), nseg, seg_off32.as<int>(), mid_list.as<int>(), kept_cnt.as<int>(),
+                       counters.as<unsigned long long>(), (long long)cap, ctrl.as<PostCtrl>());
+        launch_chained(ctx, k2_bin, ctx->sm_count * 4, 256, 0, st, keys[0].as<uint64_t>(), slot.as<uint32_t>(), cbox.as<float4>(), seg_off32.as<int>(),
+                       kl.seg_shift, ctrl.as<PostCtrl>(), bkeys.as<uint64_t>(), bbox.as<float4>());
+    }
 }
 
 void PostProc::segmented_nms(const CandSource& src, const KeyLayout& kl, float iou_thr, const StitchCtx* stc) {
@@ -554,6 +676,14 @@ void PostProc::segmented_nms(const CandSource& src, const KeyLayout& kl, float i
                        rkey.as<uint64_t>(), kept_cnt.as<int>(), C);
     }
     if (cta_possible) Y3_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+    static const bool fuse = getenv("Y3_NO_POST_FUSE") == nullptr;
+    fused_emit = fuse && A.nseg <= 16384;
+    if (fused_emit) {
+        if (stc)
+            launch_chained(ctx, k2_emit_fused, (A.nseg + 7) / 8, 256, 0, st, A, seg_off32.as<int>(), kept_cnt.as<int>(), rbox.as<float4>(),
+                           rkey.as<uint64_t>(), ctrl.as<PostCtrl>(), EmitPlain{}, stc->preds, (long long)stc->cap_rows);
+        return;                                                  // (plain: segmented_emit_plain launches it with the output arrays)
+    }
     launch_chained(ctx, k2_out_scan, 1, 1024, 0, st, kept_cnt.as<int>(), A.nseg, out_off.as<int>(), ctrl.as<PostCtrl>(), A.tiled);
     if (stc) {
         const int blocks = std::min((A.nseg + 7) / 8, ctx->sm_count * 8);
@@ -570,9 +700,14 @@ void PostProc::segmented_emit_plain(const CandSource& src, const KeyLayout& kl) 
     o_box.reserve(cap * 16); o_score.reserve(cap * 4); o_label.reserve(cap * 4); o_img.reserve(cap * 4); o_src.reserve(cap * 4);
     const SegArgs A = seg_args(src, kl, 0.f, nullptr);
     EmitPlain P{o_box.as<float4>(), o_score.as<float>(), o_label.as<int32_t>(), o_img.as<int32_t>(), o_src.as<int32_t>()};
-    const int blocks = std::min((A.nseg + 7) / 8, ctx->sm_count * 8);
-    launch_chained(ctx, k2_emit, blocks, 256, 0, st, A, seg_off32.as<int>(), kept_cnt.as<int>(), out_off.as<int>(), rbox.as<float4>(),
-                   rkey.as<uint64_t>(), ctrl.as<PostCtrl>(), P, (double*)nullptr, (long long)0);
+    if (fused_emit) {
+        launch_chained(ctx, k2_emit_fused, (A.nseg + 7) / 8, 256, 0, st, A, seg_off32.as<int>(), kept_cnt.as<int>(), rbox.as<float4>(),
+                       rkey.as<uint64_t>(), ctrl.as<PostCtrl>(), P, (double*)nullptr, (long long)0);
+    } else {
+        const int blocks = std::min((A.nseg + 7) / 8, ctx->sm_count * 8);
+        launch_chained(ctx, k2_emit, blocks, 256, 0, st, A, seg_off32.as<int>(), kept_cnt.as<int>(), out_off.as<int>(), rbox.as<float4>(),
+                       rkey.as<uint64_t>(), ctrl.as<PostCtrl>(), P, (double*)nullptr, (long long)0);
+    }
     host_ctrl.reserve(sizeof(PostCtrl));
     Y3_CUDA(cudaMemcpyAsync(host_ctrl.p, ctrl.p, sizeof(PostCtrl), cudaMemcpyDeviceToHost, st));
     pending_cap = cap;

@@ -33,7 +33,7 @@ struct PostCtrl {
     int overflow;                    // n_cand exceeded the candidate capacity
     int n_big, big_next;             // work list [0, n_big): segments one CTA resolves with the large key buffer; cursor
     int n_mid, mid_next;             // work list [n_big, n_mid): segments one CTA resolves (largest first); cursor
-    int n_small, pad0_;              // work list [n_mid, n_small): segments one warp resolves (static round-robin)
+    int n_small, emit_ticket;        // work list [n_mid, n_small): segments one warp resolves (static round-robin); blocks of the fused emit done
     int max_seg;                     // largest segment
     int n_kept;                      // boxes this run emits (tiled: after the ownership filter)
     int n_kept_nms;                  // boxes NMS kept (before the ownership filter)
@@ -126,6 +126,7 @@ struct PostProc {
     void segmented_emit_plain(const CandSource& src, const KeyLayout& kl);
     NmsResult pending;           // result of a run that completed inside enqueue()
     int64_t pending_cap = -1;    // >= 0: a plain segmented run is in flight (its candidate capacity)
+    bool fused_emit = false;     // the last segmented_nms left the output scan to k2_emit_fused
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     NmsResult run_global_sort(const CandSource& src, float iou_thr, const KeyLayout& kl, int64_t cap, int64_t K);
