@@ -23,8 +23,6 @@ struct ConvArgs {
     int has_res, linear, out_f32;
     int in_f16, in2_f16;     // operand format of the K chunks read through map_a / map_a2 (and of their weights): fp16 instead of bf16
     int out_f16;             // the output activation tensor is fp16 (the fp16 tail after the first upsample, net.cu)
-    int probe_half_b;        // measurement probe (Y3_PROBE_HALF_B): only half of each weight k-slice is loaded - WRONG results,
-                             // used once to measure how much of a layer's time is the L2->SM traffic of the weights
     int Ho, Wo;
     const float* bias;       // [cout_pad]
     const float* scale;      // [cout_pad]  gamma / sqrt(var + eps)       (unused when linear)

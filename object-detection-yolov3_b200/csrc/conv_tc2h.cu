@@ -142,7 +142,7 @@ k_conv_tc2h(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         mbar_wait(&empty[stage], phase ^ 1u);
                         unsigned char* sa = stage_base + stage * C::STAGE_BYTES;
                         const uint32_t lead_full = mapa_u32(&full[stage], 0);
-                        if (rank == 0) mbar_expect_tx(&full[stage], (uint32_t)(2 * (rows * BK * 2 + (P.probe_half_b ? C::B_BYTES / 2 : C::B_BYTES))));
+                        if (rank == 0) mbar_expect_tx(&full[stage], (uint32_t)(2 * (rows * BK * 2 + C::B_BYTES)));
                         if (P.im2col) {
                             tma2_load_im2col_4d(sa, &map_a, lead_full, kc * BK, im_w, im_h, im_n, (uint16_t)kw, (uint16_t)kh);
                         } else if (P.stride == 1) {

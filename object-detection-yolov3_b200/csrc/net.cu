@@ -443,10 +443,7 @@ void Net::make_launches(Op& op) {
             const __nv_bfloat16* wbase = op.w.as<__nv_bfloat16>() + (size_t)sub * op.cout_pad * cin;
             uint64_t dims[2] = {ktot, (uint64_t)op.cout_pad};
             uint64_t str[1] = {ktot * 2};
-            static const bool probe_half_b = getenv("Y3_PROBE_HALF_B") != nullptr;
-            A.probe_half_b = (probe_half_b && two && bn == 256 && taps == 9) ? 1 : 0;
             uint32_t box[2] = {(uint32_t)bk, (uint32_t)(two ? bn / 2 : bn)};
-            if (A.probe_half_b) box[1] /= 2;
             encode_tmap_bf16(&L.map_b, wbase, 2, dims, str, box, bk * 2);
         }
         // ---- output
