@@ -9,16 +9,26 @@
 // Ordering rule: score descending, then input row ascending (the reference's argsort()[::-1] is
 // unpinned on ties - SURVEY.md Q11 - this is the one documented deviation).
 //
-// Pipeline (all on ctx->stream):
-//   k_candidates      one thread per (row, class): threshold, ballot-compact, emit a 64-bit key
-//                     [segment | ~orderable(score) | row] and the global row as the value
+// This file holds (1) the threshold + compaction kernels shared by both pipelines and (2) the global-sort pipeline.
+// The default pipeline is the segmented, synchronisation-free one in nms_seg.cu; PostProc::enqueue() routes:
+//   every (image, class) segment can fit one CTA's shared memory (<= 24576 boxes)  -> nms_seg.cu
+//   otherwise the largest segment is read back once: still <= 24576                 -> nms_seg.cu
+//                                                    larger (e.g. 200 k boxes, 1 class) -> global sort (below)
+//
+// Threshold + compaction (all routes):
+//   k_candidates          one thread per (row, class) of decoded rows (also raw heads: the pre-round-2 form, A/B)
+//   k_candidates_heads1   raw heads, one class: one lane per row
+//   k_live_rows + k_candidates_rows   raw heads, many classes: list the rows whose objectness can pass, then one warp per
+//                         listed row.  Candidates = 64-bit key [segment | ~orderable(score) | row], the global row, the
+//                         decoded box and (segmented route) the slot inside the segment
+// Global-sort pipeline (all on ctx->stream, host-synchronised):
 //   k_rs_*            own stable LSD radix sort (8 bits / pass) on the used key bits only
 //   k_gather_sorted   boxes / areas of the sorted candidates as SoA (coalesced for the sweeps)
 //   k_seg_offsets     segment (= image x class) boundaries by binary search on the sorted keys
-//   k_nms_segments    one CTA per segment: per 512-box chunk a shared-memory IoU bitmask
+//   k_nms_small / k_nms_segments    one warp / one CTA per segment: per 512-box chunk a shared-memory IoU bitmask
 //                     (512 x 8 u64), a serial suppression sweep over it, then the chunk's kept
 //                     boxes are applied to the rest of the segment
-//   k_nms_resolve / k_nms_apply   the same two phases as separate launches for very large
+//   k_nms_resolve_next / k_nms_apply_from   the same two phases as separate launches for very large
 //                     segments, so that the apply phase uses the whole GPU
 //   k_count / k_scan / k_scatter  ordered compaction of the keep flags into the output arrays
 // The n x n/64 bitmask is never materialised in HBM.

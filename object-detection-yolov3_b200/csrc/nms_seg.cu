@@ -8,18 +8,20 @@
 //   k2_scan         one CTA: exclusive scan of the per-segment counts -> segment offsets, ONE work list of the
 //                   non-empty segments ordered by size class (largest first), overflow / largest-segment flags - all
 //                   into a device control block
-//   k2_bin          scatters the 64-bit keys into their segment's range (arrival order inside a segment)
-//   k2_nms_cta      segments of 257 .. 24576 boxes, one CTA each (device-side cursor over the work list): bitonic sort of the keys in shared
-//                                 memory, boxes gathered in sorted order, the chunked bitmask NMS of nms.cu, ordered
-//                                 compaction;
-//   k2_nms_warp     segments of <= 256 boxes, one WARP each: no sort at all - greedy NMS by selection: the
-//                                 alive box with the smallest key (= highest score, lowest row) is found with two warp
-//                                 min-reductions (REDUX), emitted, and the boxes it suppresses are cleared; picks come out
-//                                 in the reference's output order
+//   k2_bin          scatters the 64-bit keys and boxes into their segment's range (arrival order inside a segment)
+//                   (k2_scan_bin: both in one launch when the segment table fits shared memory - every block scans
+//                   the counts itself, block 0 publishes the global results)
+//   k2_nms_warp     segments of <= 128 boxes, one WARP each: no sort at all - greedy NMS by selection: the alive box
+//                   with the smallest key (= highest score, lowest row) is found with two warp min-reductions (REDUX),
+//                   emitted, and the boxes it suppresses are cleared; picks come out in the reference's output order
+//   k2_nms_cta      segments of 129 .. 24576 boxes, one CTA each (device-side cursor over the work list), on an
+//                   auxiliary stream next to the warp kernel: bitonic sort of the keys in shared memory, boxes gathered
+//                   in sorted order, the chunked bitmask NMS of nms.cu, ordered compaction
 //   k2_out_scan     one CTA: exclusive scan of the per-segment kept counts -> output offsets, totals
 //   k2_emit         one warp per segment copies its kept records to the outputs.  On the tiled path the seam
 //                   stitching (inference_tiled.py:235-301) is folded in: the ownership test runs where the kept box
 //                   is produced, and this kernel writes the final float64 [x0,y0,x1,y1,score,label] rows.
+//                   (k2_emit_fused: scan + emit in one launch for small segment tables)
 //
 // Every count (candidates, segment sizes, kept boxes, accumulated rows) stays on the device; launches use fixed grids
 // that read their bounds from the control block.  The plain entry points read the kept count back once, the tiled
