@@ -101,3 +101,29 @@ def test_k3_200k_80_classes(post):
     R = nms_c.class_wise_nms(b, o, c, 0.45, 0.1)
     G = post.per_class_nms(b, o, c, 0.45, 0.1)
     assert all(np.array_equal(x, y) for x, y in zip(R, G))
+
+
+@pytest.mark.parametrize("copies", [1, 40])
+def test_iou_decisions_at_the_threshold_edge(post, copies):
+    """Pairs whose IoU is EXACTLY the threshold, one ulp below and one ulp above it (integer boxes: IoU = 1/2, 1/3, 2/3, 3/4,
+    1/5 as exact rationals rounded once), plus degenerate boxes (zero area, reversed corners, NaN / inf coordinates).  The
+    warp route decides most pairs without the division (inter > thr*uni*(1 +- 2^-20)), the edge and the non-finite ones must
+    fall back to the exact quotient: kept sets equal the C oracle on every route (copies = 40 puts the groups, shifted
+    apart, into one segment of 440 boxes -> the CTA route)."""
+    base = []
+    for num, den in ((1, 2), (1, 3), (2, 3), (3, 4), (1, 5)):
+        # box A = [0,0,den,1] (area den), box B = [0,0,num,1] inside it: IoU = num/den
+        base.append(([0, 0, den, 1], [0, 0, num, 1], np.float32(num) / np.float32(den)))
+    rng = np.random.default_rng(3)
+    for (a, b, q) in base:
+        for thr in (q, np.nextafter(q, np.float32(0)), np.nextafter(q, np.float32(1))):
+            boxes, scores = [], []
+            for c in range(copies):
+                off = 50.0 * c
+                boxes += [[a[0] + off, a[1], a[2] + off, a[3]], [b[0] + off, b[1], b[2] + off, b[3]]]
+            boxes += [[3, 3, 3, 9], [9, 9, 5, 5], [np.nan, 0, 1, 1], [0, 0, np.inf, 1], [0, 0, 2, 2], [0, 0, 2, 2],
+                      [1e30, 1e30, 3e38, 3e38], [-3e38, -3e38, 3e38, 3e38], [7, 7, 7, 7]]
+            boxes = np.asarray(boxes, np.float32)
+            scores = pp.make_tie_free_scores(len(boxes), rng)
+            got = post.single_class_nms(boxes, scores, float(thr)).tolist()
+            assert got == nms_c.greedy_nms(boxes, scores, float(thr)), (a, b, float(thr))

@@ -27,11 +27,17 @@ def test_variant_heads(env):
     assert all(max(v) <= HEAD_TOL for v in errs.values()), errs
 
 
-def test_global_sort_pipeline_variant():
-    """Y3_NMS_GLOBAL_SORT=1: the round-1 post-processing pipeline (global radix sort, host-synchronised) is kept as the route
-    for very large segments and as an A/B switch - the NMS, detect and tiled suites must hold with it, bit for bit."""
-    p = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-k", "not k3_200k",
+@pytest.mark.parametrize("env", [{"Y3_NMS_GLOBAL_SORT": "1"}, {"Y3_NO_POST_FUSE": "1", "Y3_NO_POST_PDL": "1"}, {"Y3_SEAM_SERIAL": "1"},
+                                 {"Y3_GRAPH_MAX_BATCH": "0"}],
+                         ids=lambda e: "+".join(sorted(e)))
+def test_post_processing_pipeline_variants(env):
+    """The post-processing A/B switches: Y3_NMS_GLOBAL_SORT (round 1's global radix sort, host-synchronised: kept as the route
+    for very large segments), Y3_NO_POST_FUSE / Y3_NO_POST_PDL (separate scan / bin / out-scan / emit kernels - the form large
+    segment tables always use - without programmatic dependent launch), Y3_SEAM_SERIAL (cross-seam stage through the general
+    pipeline), Y3_GRAPH_MAX_BATCH=0 (no CUDA-graph forward).  The NMS, detect and tiled suites must hold with each, bit for bit."""
+    p = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-k", "not k3_200k and not fp32_oracle_network and not 2048",
                         os.path.join(HERE, "test_gpu_nms.py"), os.path.join(HERE, "test_gpu_tiled_e2e.py"),
-                        os.path.join(HERE, "test_gpu_net.py") + "::test_detect_pipeline_exact_on_own_boxes"],
-                       env=dict(os.environ, Y3_NMS_GLOBAL_SORT="1"), capture_output=True, text=True, timeout=900)
+                        os.path.join(HERE, "test_gpu_net.py") + "::test_detect_pipeline_exact_on_own_boxes",
+                        os.path.join(HERE, "test_gpu_net.py") + "::test_detect_image_is_the_reference_flow_in_one_call"],
+                       env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
