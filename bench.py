@@ -137,7 +137,8 @@ def cpu_baseline_run(img, edge, n_tiles_sample, threads):
         det = pp.drop_small(det, MIN_BOX)
         b, s, l = pp.class_wise_nms(det[:, :4], det[:, 4:5], det[:, 5:], IOU_THR, SCORE_THR, nms_fn=nms_c.greedy_nms)
         if b is not None:
-            tl.ghost_band_mask(b, p["rec_x"], p["rec_y"], img.shape[:2], TILE, edge)
+            with np.errstate(invalid="ignore", over="ignore"):          # random-weight boxes can be inf: the reference warns too
+                tl.ghost_band_mask(b, p["rec_x"], p["rec_y"], img.shape[:2], TILE, edge)
     dt = time.perf_counter() - t0
     return n_tiles_sample * zone / 1e6 / dt, dt
 
