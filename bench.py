@@ -479,11 +479,13 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         conv_ms = 0.0
+        tiles_done = 0
         stage = {}
         for _ in range(args.steps):
             out = step(resident)
             t = eng.timings()
             conv_ms += t["ms_conv"]
+            tiles_done += t["tiles"]
             for k in ("ms_h2d", "ms_prep", "ms_conv", "ms_decode", "ms_nms", "ms_stitch", "ms_d2h", "ms_comm"):
                 stage[k] = stage.get(k, 0.0) + t[k] / args.steps
         e1.record()
@@ -492,6 +494,7 @@ def main():
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         t = eng.timings()
+        t["tiles_per_step"] = tiles_done / args.steps            # this rank's shard (follows its measured throughput when sharded)
         return float(ms.item()) / args.steps, out, conv_ms / args.steps, t["kernels_launched"] - k0, stage, t
 
     sampler = ClockSampler(local)
@@ -511,6 +514,8 @@ def main():
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured sustained (MEASURED_PEAKS.json)" if peaks else "fallback"
     hbm = float(peaks.get("hbm_gbs", 6650.0))
+    count = tlast["tiles_per_step"]                            # tiles this rank really ran per step
+    cfg["tiles_this_rank_measured"] = count
     conv_tf = count * CONV_GF_PER_TILE * 1e9 / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     h2d = int(side * side * 2 / world) if world > 1 else side * side * 2
     # traffic of the dominant kernel: dram bytes of ONE launch from an `ncu --set full` capture, parsed into profiles/ by

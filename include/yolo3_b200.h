@@ -244,6 +244,7 @@ typedef struct {
     float reserved_;
     int64_t kernels_launched;
     int64_t candidates, kept;
+    int64_t tiles;                  /* tiles this handle processed in the last tiled call (its shard on the sharded path) */
 } y3_timings;
 y3_status y3_get_timings(y3_handle h, y3_timings* out);
 

@@ -690,6 +690,7 @@ void infer_tiled_impl(y3_handle h, const void* img, y3_dtype dt, y3_mem img_mem,
     Y3_CHECK(tile_first >= 0 && tile_count >= 0 && tile_first + tile_count <= (int64_t)geo.size(), Y3_ERR_INVALID,
              "tile range [%lld,+%lld) outside 0..%zu", (long long)tile_first, (long long)tile_count, geo.size());
     y3_timings& Tm = h->timings;
+    Tm.tiles = tile_count;
     Phase total(h, &Tm.ms_total, "y3:total");
     T->acc_rows = 0;
     *n_out = 0;
@@ -878,9 +879,16 @@ y3_status y3_infer_tiled_sharded(y3_handle h, const void* img, y3_dtype dt, y3_m
     const int rank = comm_rank(h), world = comm_size(h);
     Y3_CHECK(world <= 64, Y3_ERR_UNSUPPORTED, "more than 64 ranks");
     const int64_t n_tiles = (int64_t)plan_tiles(H, W, th, tw, edge, nullptr, nullptr).size();
-    const int64_t per = (n_tiles + world - 1) / world;                       // contiguous row-band shard of this rank
-    const int64_t first = std::min<int64_t>((int64_t)rank * per, n_tiles);
-    const int64_t count = std::min<int64_t>(per, n_tiles - first);
+    // contiguous shard of this rank: boundaries from the cumulative shares (equal at first, then following every rank's
+    // measured throughput - identical on all ranks because they are derived from the same all-gathered numbers)
+    const double* share = comm_shares(h);
+    auto boundary = [&](int r) {
+        double cum = 0;
+        for (int k = 0; k < r; ++k) cum += share[k];
+        return r >= world ? n_tiles : std::min<int64_t>(n_tiles, (int64_t)llround(cum * (double)n_tiles));
+    };
+    const int64_t first = boundary(rank);
+    const int64_t count = boundary(rank + 1) - first;
     y3_timings& Tm = h->timings;
     Tm = y3_timings{};
     *n_out = 0;
@@ -890,6 +898,8 @@ y3_status y3_infer_tiled_sharded(y3_handle h, const void* img, y3_dtype dt, y3_m
     T->shard_local.reserve((size_t)cap_local * 48);
     int64_t n_local = 0;
     bool local_overflow = false;
+    cudaEvent_t t0 = take_event(h), t1 = take_event(h);
+    Y3_CUDA(cudaEventRecord(t0, h->stream));
     try {
         infer_tiled_impl(h, img, dt, img_mem, H, W, C, th, tw, edge, first, count, min_box, iou_thr, score_thr,
                          T->shard_local.as<double>(), Y3_MEM_DEVICE, cap_local, &n_local);
@@ -899,25 +909,37 @@ y3_status y3_infer_tiled_sharded(y3_handle h, const void* img, y3_dtype dt, y3_m
         for (auto& r_ : h->phase_log) { h->event_pool.push_back(r_.a); h->event_pool.push_back(r_.b); }
         h->phase_log.clear();
     }
+    Y3_CUDA(cudaEventRecord(t1, h->stream));
+    Y3_CUDA(cudaEventSynchronize(t1));
+    float local_ms = 0.f;
+    cudaEventElapsedTime(&local_ms, t0, t1);
+    h->event_pool.push_back(t0); h->event_pool.push_back(t1);
+    Tm.tiles = count;
     Phase comm_phase(h, &Tm.ms_comm, "y3:allgather");
-    // 2. counts of every rank (a negative count flags an overflow)
-    T->shard_counts.reserve((size_t)(world + 1) * 8);
-    h->pin_small.reserve(1024);
-    long long* h_counts = h->pin_small.as<long long>();
-    h_counts[64] = local_overflow ? -(long long)std::max<int64_t>(n_local, 1) : (long long)n_local;
+    // 2. (row count, tiles, local microseconds) of every rank; a negative count flags an overflow
+    T->shard_counts.reserve((size_t)(world + 1) * 3 * 8);
+    h->pin_small.reserve(4096);
+    long long* h_counts = h->pin_small.as<long long>();            // [world][3] gathered, then [3] local
+    long long* h_mine = h_counts + 3 * 64;
+    h_mine[0] = local_overflow ? -(long long)std::max<int64_t>(n_local, 1) : (long long)n_local;
+    h_mine[1] = (long long)count;
+    h_mine[2] = (long long)(local_ms * 1000.f);
     long long* d_counts = T->shard_counts.as<long long>();
-    Y3_CUDA(cudaMemcpyAsync(d_counts + world, h_counts + 64, 8, cudaMemcpyHostToDevice, h->stream));
-    comm_all_gather_i64(h, d_counts + world, d_counts, 1);
-    Y3_CUDA(cudaMemcpyAsync(h_counts, d_counts, (size_t)world * 8, cudaMemcpyDeviceToHost, h->stream));
+    Y3_CUDA(cudaMemcpyAsync(d_counts + 3 * world, h_mine, 24, cudaMemcpyHostToDevice, h->stream));
+    comm_all_gather_i64(h, d_counts + 3 * world, d_counts, 3);
+    Y3_CUDA(cudaMemcpyAsync(h_counts, d_counts, (size_t)world * 24, cudaMemcpyDeviceToHost, h->stream));
     Y3_CUDA(cudaStreamSynchronize(h->stream));
     long long total = 0, max_c = 0;
     bool any_overflow = false;
+    long long g_tiles[64], g_micros[64], g_rows[64];
     for (int r = 0; r < world; ++r) {
-        const long long c = h_counts[r];
+        const long long c = h_counts[3 * r];
+        g_rows[r] = c; g_tiles[r] = h_counts[3 * r + 1]; g_micros[r] = h_counts[3 * r + 2];
         if (c < 0) any_overflow = true;
         total += c < 0 ? -c : c;
         max_c = std::max(max_c, c);
     }
+    comm_update_shares(h, g_tiles, g_micros);                      // for the next call
     *n_out = total;
     Y3_CHECK(!any_overflow && total <= cap, Y3_ERR_NOSPACE, "output capacity %lld < %lld boxes", (long long)cap, total);
     if (total > 0) {
@@ -930,10 +952,10 @@ y3_status y3_infer_tiled_sharded(y3_handle h, const void* img, y3_dtype dt, y3_m
         double* dst = to_caller ? preds : T->acc.as<double>();
         long long off = 0;
         for (int r = 0; r < world; ++r) {
-            if (h_counts[r] > 0)
-                Y3_CUDA(cudaMemcpyAsync(dst + off * 6, T->shard_gather.as<double>() + (size_t)r * max_c * 6, (size_t)h_counts[r] * 48,
+            if (g_rows[r] > 0)
+                Y3_CUDA(cudaMemcpyAsync(dst + off * 6, T->shard_gather.as<double>() + (size_t)r * max_c * 6, (size_t)g_rows[r] * 48,
                                         cudaMemcpyDeviceToDevice, h->stream));
-            off += h_counts[r];
+            off += g_rows[r];
         }
         int64_t n_final = total;
         const double* final_dev = dst;

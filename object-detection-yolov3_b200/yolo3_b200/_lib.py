@@ -28,7 +28,7 @@ class Y3Timings(ctypes.Structure):
     _fields_ = [("ms_total", c_float), ("ms_h2d", c_float), ("ms_prep", c_float), ("ms_conv", c_float),
                 ("ms_decode", c_float), ("ms_nms", c_float), ("ms_stitch", c_float), ("ms_d2h", c_float),
                 ("ms_comm", c_float), ("reserved_", c_float),
-                ("kernels_launched", c_int64), ("candidates", c_int64), ("kept", c_int64)]
+                ("kernels_launched", c_int64), ("candidates", c_int64), ("kept", c_int64), ("tiles", c_int64)]
 
 
 # name -> (restype, argtypes); exactly the symbols include/yolo3_b200.h declares
