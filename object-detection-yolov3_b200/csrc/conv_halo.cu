@@ -63,7 +63,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #if defined(__CUDA_ARCH_FEAT_SM100_ALL) || defined(__CUDA_ARCH_FEAT_SM101_ALL)
     using C = HaloCfg<CIN, COUT, STRIDE>;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* smem = align_smem_1024(smem_raw);
     unsigned char* w_base = smem;
     unsigned char* ring = smem + C::W_BYTES;
     unsigned char* stg_base = ring + C::S * C::SLOT;

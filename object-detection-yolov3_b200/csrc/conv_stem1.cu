@@ -8,11 +8,12 @@
 //   stem warps (8)   gather: thread = one stem column, two stem rows per step; the 9 taps (+ two 1.0 columns that
 //                    carry the bias, as in stem_tc.cu) go as bf16 rows into four NO-SWIZZLE K-major A tiles
 //                    (row parity x column parity, 128 pixels x K = 16 each)
-//   MMA thread       stem UMMAs (M = 256 per CTA pair, N = 32, K = 16) into TMEM, then the conv2d_1 UMMAs of the
-//                    tile whose ring rows are complete (weights stationary, taps by descriptor, as conv_halo.cu)
+//   stem MMA thread  stem UMMAs (M = 256 per CTA pair, N = 32, K = 16) into TMEM
 //   stem warps       drain the stem accumulators: leaky -> scale/shift -> bf16 -> straight into the K-major
 //                    SWIZZLE_64B ring the conv2d_1 UMMAs read (stem pixels outside the image are written as zeros:
 //                    they are conv2d_1's "SAME" padding, 0 before / 1 after)
+//   conv MMA thread  conv2d_1 UMMAs of the tile whose ring rows are complete (weights stationary, taps by
+//                    descriptor, as conv_halo.cu)
 //   epilogue warps   conv2d_1: bias -> leaky -> BN -> bf16 -> staging -> TMA store
 //
 //   * a conv2d_1 tile = 128 output pixels of one row; it needs stem rows 2h, 2h+1, 2h+2 and stem columns
@@ -20,10 +21,14 @@
 //     O[128][32] (odd columns), so that tap dx = 0 / 1 / 2 is E, O, E shifted by one row of the swizzled tile.
 //     Going down a column of tiles, step g of a run produces stem rows 2(h0+g)-1 and 2(h0+g) (only the second one
 //     for g = 0), i.e. each new tile costs two new stem rows.  The 257th column of a ring row (E row 128) is
-//     computed by one warp on the FP32 pipe, one channel per lane.
+//     computed by a warp of its own on the FP32 pipe, one channel per lane.
 //   * two CTAs (images 2*ip and 2*ip+1, same column, same rows) form every UMMA (cta_group::2); each holds half
-//     of both weight matrices.  Barriers that collect generic-proxy writes of both CTAs live in the leader and
-//     count the 16 stem warps.
+//     of both weight matrices.  Barriers that collect generic-proxy writes of both CTAs live in the leader.
+//   * the step loop is a chain of latencies, not of work (a clock64 trace of the first version: 5150 cycles per
+//     step, of which the stem warps spent 1650 waiting for their own UMMA, the MMA thread 2600 issuing 22 UMMAs
+//     and the 257th column 1050 on the critical warp).  So: the stem warps write the A rows of step g+1 BEFORE
+//     they drain step g (taps prefetched one step ahead), the two UMMA streams are issued by two threads, and
+//     the 257th column has its own warp.
 #include "conv_tc.cuh"
 #include "ptx.cuh"
 #include <stdlib.h>
@@ -32,10 +37,10 @@
 namespace y3 {
 using namespace ptx;
 
-static constexpr int SC_STEM_GROUPS = 1;                  // groups of 8 stem warps; group g owns the stem steps with (step & 1) == g
-static constexpr int SC_STEM_WARPS = 8 * SC_STEM_GROUPS;
+static constexpr int SC_STEM_WARPS = 8;
 static constexpr int SC_EPI_WARPS = 8;                    // two groups of 4: group e drains the tiles with (tile & 1) == e
-static constexpr int SC_THREADS = 64 + 32 * SC_EPI_WARPS + 32 * SC_STEM_WARPS;
+static constexpr int SC_THREADS = 64 + 32 * SC_EPI_WARPS + 32 * SC_STEM_WARPS + 32;   // + the 257th-column warp
+static constexpr int SC_FULL_ARRIVALS = 2 * (SC_STEM_WARPS + 1);
 
 struct SCfg {
     static constexpr int CIN = 32, COUT = 64, ROWB = 64;
@@ -87,11 +92,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_interleaved(uint32_t saddr, u
 }
 
 // Passed by value (__grid_constant__): the stem parameters travel in the kernel parameters.
+#ifdef Y3_STEM_TRACE
+#define TR(role, step, pt) do { if (dbgp && blockIdx.x == 0 && (step) >= 64 && (step) < 80) dbgp[((role) * 16 + ((step) - 64)) * 8 + (pt)] = clock64(); } while (0)
+#else
+#define TR(role, step, pt) do { } while (0)
+#endif
 struct StemArgs {
     float w[9 * 32];          // [tap][channel]
     float bias[32], scale[32], shift[32];
     const float* in;          // [n_img][H][W] fp32 (one channel)
     int H, W;
+    long long* dbg;           // Y3_STEM_TRACE builds only
 };
 
 // the 4 x 3 image window of two vertically adjacent stem pixels (rows y0, y0+1) in column c (zeros outside the image)
@@ -140,6 +151,39 @@ __device__ __forceinline__ void stem_pixel_by_lanes(const float* __restrict__ im
     }
 }
 
+// Walks the stem steps of one CTA pair in order.  The pair's conv2d_1 tiles [t_begin, t_end) (index = column * Ho + row)
+// fall into runs down one column; a run of len tiles has len + 1 steps: step g produces the stem rows 2(h0+g)-1 and
+// 2(h0+g) (g = 0: only the second) into the ring rows k (and k + 1).
+struct Steps {
+    int t_end, Ho, tiles_x;
+    int t, h0, len, g;         // run: first tile, its row, tiles; position inside the run
+    int ip, w0;                // run: image pair, first conv2d_1 output column
+    int gs, k;                 // global step counter; ring row index of the step's first produced row
+    __device__ __forceinline__ void start_run() {
+        if (t < t_end) {
+            const int col = t / Ho;
+            h0 = t - col * Ho;
+            len = min(t_end - t, Ho - h0);
+            ip = col / tiles_x;
+            w0 = (col - ip * tiles_x) * 128;
+            g = 0;
+        }
+    }
+    __device__ __forceinline__ void init(int t_begin, int t_end_, int Ho_, int tiles_x_) {
+        t_end = t_end_; Ho = Ho_; tiles_x = tiles_x_; t = t_begin; gs = 0; k = 0;
+        h0 = len = g = ip = w0 = 0;
+        start_run();
+    }
+    __device__ __forceinline__ bool done() const { return t >= t_end; }
+    __device__ __forceinline__ void next() {
+        k += g == 0 ? 1 : 2;
+        ++gs;
+        if (++g > len) { t += len; start_run(); }
+    }
+    __device__ __forceinline__ int first() const { return g == 0; }
+    __device__ __forceinline__ int y0() const { return 2 * (h0 + g) - 1; }      // stem rows y0 (unused when first) and y0 + 1
+};
+
 // what the stem warps remember about the step whose accumulators they still have to drain
 struct StepInfo {
     int valid, buf, y0, w0, k, first;      // k = ring row index of the step's first produced row
@@ -151,8 +195,9 @@ k_stem_conv1(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ 
              const __grid_constant__ StemArgs T) {
 #if defined(__CUDA_ARCH_FEAT_SM100_ALL) || defined(__CUDA_ARCH_FEAT_SM101_ALL)
     using C = SCfg;
+    long long* const dbgp = T.dbg; (void)dbgp;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* smem = align_smem_1024(smem_raw);
     unsigned char* w_base = smem;
     unsigned char* ring = smem + C::W_BYTES;
     unsigned char* stg_base = ring + C::S * C::SLOT;
@@ -162,7 +207,7 @@ k_stem_conv1(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ 
     float* s_w = s_par + 3 * C::COUT;                                         // stem weights [9][32] fp32 (257th pixel)
     float* s_sp = s_w + 9 * 32;                                               // stem bias | scale | shift
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_par + C::PAR_FLOATS);
-    uint64_t* full = bars;                       // leader only: 16 stem warps (both CTAs) arrive per ring row
+    uint64_t* full = bars;                       // leader only: the stem warps and the 257th-column warp of both CTAs arrive per ring row
     uint64_t* empty = bars + C::S;               // per CTA, multicast commit
     uint64_t* tmem_full = bars + 2 * C::S;       // per CTA, multicast commit
     uint64_t* tmem_empty = tmem_full + 2;        // leader only
@@ -181,7 +226,7 @@ k_stem_conv1(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) { prefetch_tmap(&map_b); prefetch_tmap(&map_out); }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < C::S; ++s) { mbar_init(&full[s], 16); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < C::S; ++s) { mbar_init(&full[s], SC_FULL_ARRIVALS); mbar_init(&empty[s], 1); }
         for (int p = 0; p < 2; ++p) {
             mbar_init(&tmem_full[p], 1); mbar_init(&tmem_empty[p], 8);
             mbar_init(&sa_full[p], 16); mbar_init(&sa_empty[p], 1);
@@ -230,100 +275,121 @@ k_stem_conv1(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ 
     const int t_end = (int)(total * (pair + 1) / n_pairs);
 
     if (warp == 0) {
-        // ------------------------------------------------------------ conv2d_1 weights (stationary)
+        // ------------------------------------------------------------ conv2d_1 weights (stationary), then the stem UMMAs
         if (lane == 0) {
             const uint32_t lead_w = mapa_u32(w_full, 0);
             if (rank == 0) mbar_expect_tx(w_full, (uint32_t)(2 * C::W_BYTES));
             for (int tap = 0; tap < 9; ++tap)
                 tma2_load_2d(w_base + tap * C::WTAP, &map_b, lead_w, tap * C::CIN, (int)rank * (C::COUT / 2));
         }
+        if (rank == 0 && lane == 0) {
+            constexpr uint32_t idesc_stem = make_idesc_bf16(256, 32);
+            const uint64_t sb_desc = make_smem_desc_interleaved(smem_u32(sb_base), 128, 256);
+            Steps st;
+            for (st.init(t_begin, t_end, Ho, P.tiles_x); !st.done(); st.next()) {
+                const int buf = st.gs & 1;
+                const uint32_t use = (uint32_t)(st.gs >> 1);
+                TR(0, st.gs, 0);
+                mbar_wait(&sacc_empty[buf], (use & 1u) ^ 1u);
+                mbar_wait(&sa_full[buf], use & 1u);
+                TR(0, st.gs, 1);
+                tc_fence_after();
+#pragma unroll
+                for (int tile = 0; tile < 4; ++tile) {
+                    const uint64_t adesc = make_smem_desc_interleaved(smem_u32(sa_base + buf * C::SA_BUF + tile * C::SA_TILE), 128, 256);
+                    umma2_bf16(tmem_base + C::STEM_COL0 + (uint32_t)(buf * 128 + tile * 32), adesc, sb_desc, idesc_stem, 0u);
+                }
+                umma2_commit_mc(&sacc_full[buf], 3);
+                umma2_commit_mc(&sa_empty[buf], 3);
+                TR(0, st.gs, 2);
+            }
+        }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer: leader CTA, one thread
+        // ------------------------------------------------------------ conv2d_1 MMA issuer: leader CTA, one thread
         if (rank == 0 && lane == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(256, C::COUT);
-            constexpr uint32_t idesc_stem = make_idesc_bf16(256, 32);
             mbar_wait(w_full, 0);
             tc_fence_after();
             const uint32_t w_addr = smem_u32(w_base);
             const uint32_t ring_addr = smem_u32(ring);
-            const uint64_t sb_desc = make_smem_desc_interleaved(smem_u32(sb_base), 128, 256);
             int it = 0;                 // conv2d_1 tile counter
-            int gs = 0;                 // global stem step counter
-            int k_run = 0;              // ring row index of the current run's first row
-            // conv2d_1 tile that becomes issuable once the NEXT stem step has been issued (one-step lag keeps the
-            // stem one step ahead of the convolution)
-            int pend = 0, pend_k0 = 0, pend_r = 0, pend_last = 0;
-            auto issue_conv = [&](int k0, int r, int last) {
-                const int p = it & 1;
-                const uint32_t use = (uint32_t)(it >> 1);
-                mbar_wait(&tmem_empty[p], (use & 1u) ^ 1u);
-                for (int dy = (r == 0 ? 0 : 1); dy < 3; ++dy) {
-                    const int kk = k0 + 2 * r + dy;
-                    mbar_wait(&full[kk % C::S], (uint32_t)((kk / C::S) & 1));
-                }
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(p * C::COUT);
-#pragma unroll
-                for (int dy = 0; dy < 3; ++dy) {
-                    const uint32_t slot_addr = ring_addr + (uint32_t)(((k0 + 2 * r + dy) % C::S) * C::SLOT);
-#pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        // dx = 0: even columns; dx = 1: odd columns; dx = 2: even columns shifted by one pixel
-                        const uint32_t a_addr = slot_addr + (dx == 1 ? (uint32_t)C::E_BYTES : (dx == 2 ? (uint32_t)C::ROWB : 0u));
-                        const uint64_t adesc = make_smem_desc(a_addr, C::SBO, SWZ_64B);
-                        const uint64_t bdesc = make_smem_desc(w_addr + (uint32_t)((dy * 3 + dx) * C::WTAP), C::SBO, SWZ_64B);
-#pragma unroll
-                        for (int kc = 0; kc < C::CIN / 16; ++kc)
-                            umma2_bf16(d_tmem, adesc + (uint64_t)(kc * 2), bdesc + (uint64_t)(kc * 2), idesc, (uint32_t)((dy | dx | kc) != 0));
-                    }
-                }
-                umma2_commit_mc(&tmem_full[p], 3);
-                umma2_commit_mc(&empty[(k0 + 2 * r) % C::S], 3);
-                umma2_commit_mc(&empty[(k0 + 2 * r + 1) % C::S], 3);
-                if (last) umma2_commit_mc(&empty[(k0 + 2 * r + 2) % C::S], 3);
-                ++it;
-            };
+            int k0 = 0;                 // ring row index of the current run's first row
             for (int t = t_begin; t < t_end;) {
                 const int col = t / Ho;
                 const int h0 = t - col * Ho;
                 const int len = min(t_end - t, Ho - h0);
-                for (int g = 0; g <= len; ++g, ++gs) {
-                    const int buf = gs & 1;
-                    const uint32_t use = (uint32_t)(gs >> 1);
-                    mbar_wait(&sacc_empty[buf], (use & 1u) ^ 1u);
-                    mbar_wait(&sa_full[buf], use & 1u);
-                    tc_fence_after();
-#pragma unroll
-                    for (int tile = 0; tile < 4; ++tile) {
-                        const uint64_t adesc = make_smem_desc_interleaved(smem_u32(sa_base + buf * C::SA_BUF + tile * C::SA_TILE), 128, 256);
-                        umma2_bf16(tmem_base + C::STEM_COL0 + (uint32_t)(buf * 128 + tile * 32), adesc, sb_desc, idesc_stem, 0u);
+                for (int r = 0; r < len; ++r, ++it) {
+                    const int p = it & 1;
+                    const uint32_t use = (uint32_t)(it >> 1);
+                    TR(3, it, 0);
+                    mbar_wait(&tmem_empty[p], (use & 1u) ^ 1u);
+                    TR(3, it, 1);
+                    for (int dy = (r == 0 ? 0 : 1); dy < 3; ++dy) {
+                        const int kk = k0 + 2 * r + dy;
+                        mbar_wait(&full[kk % C::S], (uint32_t)((kk / C::S) & 1));
                     }
-                    umma2_commit_mc(&sa_empty[buf], 3);
-                    umma2_commit_mc(&sacc_full[buf], 3);
-                    if (pend) { issue_conv(pend_k0, pend_r, pend_last); pend = 0; }
-                    if (g >= 1) { pend = 1; pend_k0 = k_run; pend_r = g - 1; pend_last = (g == len); }
+                    TR(3, it, 2);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(p * C::COUT);
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const uint32_t slot_addr = ring_addr + (uint32_t)(((k0 + 2 * r + dy) % C::S) * C::SLOT);
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            // dx = 0: even columns; dx = 1: odd columns; dx = 2: even columns shifted by one pixel
+                            const uint32_t a_addr = slot_addr + (dx == 1 ? (uint32_t)C::E_BYTES : (dx == 2 ? (uint32_t)C::ROWB : 0u));
+                            const uint64_t adesc = make_smem_desc(a_addr, C::SBO, SWZ_64B);
+                            const uint64_t bdesc = make_smem_desc(w_addr + (uint32_t)((dy * 3 + dx) * C::WTAP), C::SBO, SWZ_64B);
+#pragma unroll
+                            for (int kc = 0; kc < C::CIN / 16; ++kc)
+                                umma2_bf16(d_tmem, adesc + (uint64_t)(kc * 2), bdesc + (uint64_t)(kc * 2), idesc, (uint32_t)((dy | dx | kc) != 0));
+                        }
+                    }
+                    umma2_commit_mc(&tmem_full[p], 3);
+                    umma2_commit_mc(&empty[(k0 + 2 * r) % C::S], 3);
+                    umma2_commit_mc(&empty[(k0 + 2 * r + 1) % C::S], 3);
+                    if (r == len - 1) umma2_commit_mc(&empty[(k0 + 2 * r + 2) % C::S], 3);
+                    TR(3, it, 3);
                 }
-                k_run += 2 * len + 1;
+                k0 += 2 * len + 1;
                 t += len;
             }
-            if (pend) issue_conv(pend_k0, pend_r, pend_last);
+        }
+    } else if (warp == 2 + SC_EPI_WARPS + SC_STEM_WARPS) {
+        // ------------------------------------------------------------ 257th stem column of every ring row (E row 128)
+        const int H = T.H, W = T.W;
+        Steps st;
+        for (st.init(t_begin, t_end, Ho, P.tiles_x); !st.done(); st.next()) {
+            const int img = 2 * st.ip + (int)rank;
+            const bool img_ok = img < P.n_img;
+            const float* imgp = T.in + (long long)(img_ok ? img : 0) * H * W;
+            const int first = st.first();
+            const int k_q0 = st.k, k_q1 = first ? st.k : st.k + 1;
+            if (!first) mbar_wait(&empty[k_q0 % C::S], (uint32_t)(((k_q0 / C::S) & 1) ^ 1));
+            mbar_wait(&empty[k_q1 % C::S], (uint32_t)(((k_q1 / C::S) & 1) ^ 1));
+            unsigned char* const re[2] = {ring + (k_q0 % C::S) * C::SLOT + 128 * C::ROWB, ring + (k_q1 % C::S) * C::SLOT + 128 * C::ROWB};
+            stem_pixel_by_lanes(imgp, img_ok, H, W, st.y0(), 2 * st.w0 + 256, s_w, s_sp, lane, re, first != 0);
+            fence_proxy_async_smem();              // generic-proxy writes -> visible to the tensor core's reads
+            __syncwarp();
+            if (lane == 0) {
+                if (!first) mbar_arrive_cluster(mapa_u32(&full[k_q0 % C::S], 0));
+                mbar_arrive_cluster(mapa_u32(&full[k_q1 % C::S], 0));
+            }
         }
     } else if (warp >= 2 + SC_EPI_WARPS) {
         // ------------------------------------------------------------ stem warps
-        const int sw_all = warp - (2 + SC_EPI_WARPS);
-        const int grp = sw_all >> 3;                            // this warp's group: it works on steps with (gs & 1) == grp
-        const int sw = sw_all & 7;
-        const int st = sw * 32 + lane;                          // 0..255 = stem column offset inside the tile's 257 columns
+        const int sw = warp - (2 + SC_EPI_WARPS);
+        const int st_col = sw * 32 + lane;                      // 0..255 = stem column offset inside the tile's 257 columns
         const int qd = warp & 3;                                // TMEM lane quadrant of this warp
         const int hi = sw >> 2;                                 // stem row of a step (0 / 1) this warp drains
-        const int j = st >> 1, par = st & 1;
+        const int j = st_col >> 1, par = st_col & 1;
         const int H = T.H, W = T.W;
-        int k = 0, gs = 0;
-        StepInfo prev;
-        prev.valid = 0;
+        const bool tr_on = lane == 0 && (sw == 0 || sw == 7);
+        const int tr_role = sw == 0 ? 1 : 2; (void)tr_role; (void)tr_on;
         // drain the accumulators of a finished stem step into the ring
-        auto drain = [&](const StepInfo& s, const float* imgp, bool img_ok) {
+        auto drain = [&](const StepInfo& s, int gs_now) {
             mbar_wait(&sacc_full[s.buf], s.use & 1u);
+            if (tr_on) TR(tr_role, gs_now, 2);
             tc_fence_after();
             const bool mine = !(s.first && hi == 0);            // step 0 of a run: its first stem row is not needed
             const uint32_t t_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + C::STEM_COL0 + (uint32_t)(s.buf * 128 + hi * 64);
@@ -331,7 +397,8 @@ k_stem_conv1(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ 
             const int k_q0 = s.k, k_q1 = s.first ? s.k : s.k + 1;
             if (!s.first) mbar_wait(&empty[k_q0 % C::S], (uint32_t)(((k_q0 / C::S) & 1) ^ 1));
             mbar_wait(&empty[k_q1 % C::S], (uint32_t)(((k_q1 / C::S) & 1) ^ 1));
-            unsigned char* slot_q[2] = {ring + (k_q0 % C::S) * C::SLOT, ring + (k_q1 % C::S) * C::SLOT};
+            unsigned char* const slot_mine = ring + ((hi ? k_q1 : k_q0) % C::S) * C::SLOT;      // the ring row this warp writes
+            if (tr_on) TR(tr_role, gs_now, 3);
             if (mine) {
                 const int y = s.y0 + hi;
                 const int px = qd * 32 + lane;                  // pixel index inside the E / O array
@@ -341,8 +408,9 @@ k_stem_conv1(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ 
                     uint32_t v[32];
                     tmem_ld_32x32(t_addr + (uint32_t)(pp * 32), v);
                     tmem_ld_wait();
+                    if (tr_on) TR(tr_role, gs_now, 4 + 2 * pp);
                     const bool inside = (y < H) && (2 * s.w0 + 2 * px + pp < W);
-                    unsigned char* rowp = slot_q[hi] + (pp ? C::E_BYTES : 0) + px * C::ROWB;
+                    unsigned char* rowp = slot_mine + (pp ? C::E_BYTES : 0) + px * C::ROWB;
 #pragma unroll
                     for (int c16 = 0; c16 < 4; ++c16) {
                         uint32_t o[4];
@@ -357,69 +425,72 @@ k_stem_conv1(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ 
                         }
                         *reinterpret_cast<uint4*>(rowp + ((c16 ^ swz) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
                     }
+                    if (tr_on && pp == 0) TR(tr_role, gs_now, 5);
                 }
             }
             tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_u32(&sacc_empty[s.buf], 0));
-            if (sw == 7) {
-                unsigned char* const re[2] = {slot_q[0] + 128 * C::ROWB, slot_q[1] + 128 * C::ROWB};
-                stem_pixel_by_lanes(imgp, img_ok, H, W, s.y0, 2 * s.w0 + 256, s_w, s_sp, lane, re, s.first != 0);
-            }
             fence_proxy_async_smem();              // generic-proxy writes -> visible to the tensor core's reads
             __syncwarp();
             if (lane == 0) {
+                mbar_arrive_cluster(mapa_u32(&sacc_empty[s.buf], 0));
                 if (!s.first) mbar_arrive_cluster(mapa_u32(&full[k_q0 % C::S], 0));
                 mbar_arrive_cluster(mapa_u32(&full[k_q1 % C::S], 0));
             }
+            if (tr_on) TR(tr_role, gs_now, 7);
         };
-        const float* imgp_prev = T.in;
-        bool img_ok_prev = false;
-        for (int t = t_begin; t < t_end;) {
-            const int col = t / Ho;
-            const int h0 = t - col * Ho;
-            const int len = min(t_end - t, Ho - h0);
-            const int ip = col / P.tiles_x;
-            const int w0 = (col - ip * P.tiles_x) * 128;
-            const int img = 2 * ip + (int)rank;
+        auto taps_of = [&](const Steps& q, float (&tp)[4][3]) {
+            const int img = 2 * q.ip + (int)rank;
             const bool img_ok = img < P.n_img;
             const float* imgp = T.in + (long long)(img_ok ? img : 0) * H * W;
-            const int c = 2 * w0 + st;
-            for (int g = 0; g <= len; ++g, ++gs) {
-                const int nrows = (g == 0) ? 1 : 2;
-                if (SC_STEM_GROUPS == 2 && (gs & 1) != grp) { k += nrows; continue; }  // the other group's step
-                const int buf = gs & 1;
-                const uint32_t use = (uint32_t)(gs >> 1);
-                const int y0 = 2 * (h0 + g) - 1;                // stem rows y0 (unused when g = 0) and y0 + 1
-                float tp[4][3];
-                stem_taps(imgp, img_ok, H, W, y0, c, tp);       // in flight while the previous step is drained
-                if (prev.valid) drain(prev, imgp_prev, img_ok_prev);
-                mbar_wait(&sa_empty[buf], (use & 1u) ^ 1u);
-                // A rows of the two stem pixels of this column: K = taps 0..8, 1.0, 1.0, zeros (interleaved layout)
+            stem_taps(imgp, img_ok, H, W, q.y0(), 2 * q.w0 + st_col, tp);
+        };
+        Steps st;
+        st.init(t_begin, t_end, Ho, P.tiles_x);
+        StepInfo prev;
+        prev.valid = 0;
+        float tp[4][3];
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    unsigned char* rowp = sa_base + buf * C::SA_BUF + (q * 2 + par) * C::SA_TILE + (j >> 3) * 256 + (j & 7) * 16;
-                    *reinterpret_cast<uint4*>(rowp) = make_uint4(pack2s(tp[q][0], tp[q][1]), pack2s(tp[q][2], tp[q + 1][0]),
-                                                                  pack2s(tp[q + 1][1], tp[q + 1][2]), pack2s(tp[q + 2][0], tp[q + 2][1]));
-                    *reinterpret_cast<uint4*>(rowp + 128) = make_uint4(pack2s(tp[q + 2][2], 1.0f), pack2s(1.0f, 0.f), 0u, 0u);
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(mapa_u32(&sa_full[buf], 0));
-                prev.valid = 1; prev.buf = buf; prev.use = use; prev.y0 = y0; prev.w0 = w0; prev.k = k; prev.first = (g == 0);
-                imgp_prev = imgp; img_ok_prev = img_ok;
-                k += nrows;
+        for (int rr = 0; rr < 4; ++rr) tp[rr][0] = tp[rr][1] = tp[rr][2] = 0.f;
+        if (!st.done()) taps_of(st, tp);
+        while (!st.done()) {
+            const int buf = st.gs & 1;
+            const uint32_t use = (uint32_t)(st.gs >> 1);
+            StepInfo cur;
+            cur.valid = 1; cur.buf = buf; cur.use = use; cur.y0 = st.y0(); cur.w0 = st.w0; cur.k = st.k; cur.first = st.first();
+            const int gs_now = st.gs;
+            st.next();
+            if (tr_on) TR(tr_role, gs_now, 0);
+            mbar_wait(&sa_empty[buf], (use & 1u) ^ 1u);
+            // A rows of the two stem pixels of this column: K = taps 0..8, 1.0, 1.0, zeros (interleaved layout)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                unsigned char* rowp = sa_base + buf * C::SA_BUF + (q * 2 + par) * C::SA_TILE + (j >> 3) * 256 + (j & 7) * 16;
+                *reinterpret_cast<uint4*>(rowp) = make_uint4(pack2s(tp[q][0], tp[q][1]), pack2s(tp[q][2], tp[q + 1][0]),
+                                                              pack2s(tp[q + 1][1], tp[q + 1][2]), pack2s(tp[q + 2][0], tp[q + 2][1]));
+                *reinterpret_cast<uint4*>(rowp + 128) = make_uint4(pack2s(tp[q + 2][2], 1.0f), pack2s(1.0f, 0.f), 0u, 0u);
             }
-            t += len;
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(&sa_full[buf], 0));
+            if (tr_on) TR(tr_role, gs_now, 1);
+            // the NEXT step's taps: requested after the fence above (it would wait for them) and in flight while the
+            // previous step is drained
+            float tn[4][3];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) tn[rr][0] = tn[rr][1] = tn[rr][2] = 0.f;
+            if (!st.done()) taps_of(st, tn);
+            if (prev.valid) drain(prev, gs_now);                // the previous step: its UMMAs were issued an iteration ago
+            prev = cur;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) { tp[rr][0] = tn[rr][0]; tp[rr][1] = tn[rr][1]; tp[rr][2] = tn[rr][2]; }
         }
-        if (prev.valid) drain(prev, imgp_prev, img_ok_prev);
+        if (prev.valid) drain(prev, -1);
         // tail: multicast commits from the leader may still arrive on this CTA's barriers
         if (sw == 0 && lane == 0) {
-            if (grp == 0)
-                for (int jx = 0; jx < C::S; ++jx, ++k) mbar_wait(&empty[k % C::S], (uint32_t)(((k / C::S) & 1) ^ 1));
+            int k = st.k;
+            for (int jx = 0; jx < C::S; ++jx, ++k) mbar_wait(&empty[k % C::S], (uint32_t)(((k / C::S) & 1) ^ 1));
             for (int b = 0; b < 2; ++b) {
-                if (SC_STEM_GROUPS == 2 && b != grp) continue;
-                const int gnext = gs + (((gs & 1) != b) ? 1 : 0);      // next step that would use A buffer b
+                const int gnext = st.gs + (((st.gs & 1) != b) ? 1 : 0);      // next step that would use A buffer b
                 mbar_wait(&sa_empty[b], (uint32_t)(((gnext >> 1) & 1) ^ 1));
             }
         }
@@ -439,7 +510,9 @@ k_stem_conv1(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ 
             const int img = 2 * ip + (int)rank;
             const int p = it & 1;
             const uint32_t use = (uint32_t)(it >> 1);
+            if (elected && eg == 0) TR(4, it, 0);
             mbar_wait(&tmem_full[p], use & 1u);
+            if (elected && eg == 0) TR(4, it, 1);
             tc_fence_after();
             unsigned char* stg = stg_base + p * C::STG_BYTES;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * C::COUT);
@@ -479,14 +552,18 @@ k_stem_conv1(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[p], 0));
+            if (elected && eg == 0) TR(4, it, 2);
             fence_proxy_async_smem();
             named_bar_sync(1 + eg, 128);
+            if (elected && eg == 0) TR(4, it, 3);
             if (elected) {
                 if (img < P.n_img) tma_store_4d(&map_out, stg, 0, w0, h, img);
                 tma_store_commit();
                 tma_store_wait_read();             // this group's staging buffer is free again for its next tile
             }
+            if (elected && eg == 0) TR(4, it, 4);
             named_bar_sync(1 + eg, 128);
+            if (elected && eg == 0) TR(4, it, 5);
         }
     }
     tc_fence_before();
@@ -514,10 +591,33 @@ void launch_stem_conv1(y3_context* ctx, const ConvLaunch& L, const float* in, co
     memcpy(T.scale, stem_scale_host, sizeof(T.scale));
     memcpy(T.shift, stem_shift_host, sizeof(T.shift));
     T.in = in; T.H = H; T.W = W;
+    T.dbg = nullptr;
+#ifdef Y3_STEM_TRACE
+    static long long* d_dbg = nullptr;
+    if (!d_dbg) { cudaError_t e = cudaMalloc(&d_dbg, 65536); fprintf(stderr, "trace buffer %p (%s)\n", (void*)d_dbg, cudaGetErrorString(e)); }
+    cudaMemsetAsync(d_dbg, 0, 65536, ctx->stream);
+    T.dbg = d_dbg;
+#endif
     const long long total = (long long)((A.n_img + 1) / 2) * A.tiles_x * A.Ho;
     const int pairs = (int)std::min<long long>(total, (long long)(ctx->sm_count / 2));
     k_stem_conv1<<<2 * pairs, SC_THREADS, SCfg::SMEM, ctx->stream>>>(L.map_b, L.map_out, L.args, T);
     Y3_LAUNCHED(ctx);
+#ifdef Y3_STEM_TRACE
+    static int traced = 0;
+    if (++traced == 3) {
+        long long hbuf[5 * 16 * 8];
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(hbuf, d_dbg, sizeof(hbuf), cudaMemcpyDeviceToHost);
+        long long base = hbuf[0];
+        const char* roles[5] = {"mma", "stem0", "stem7", "epi0", "epi1"};
+        for (int r = 0; r < 5; ++r)
+            for (int st = 0; st < 16; ++st) {
+                fprintf(stderr, "TRACE %-6s step %2d:", roles[r], 64 + st);
+                for (int p = 0; p < 8; ++p) fprintf(stderr, " %7lld", hbuf[(r * 16 + st) * 8 + p] ? hbuf[(r * 16 + st) * 8 + p] - base : -1LL);
+                fprintf(stderr, "\n");
+            }
+    }
+#endif
 }
 
 }  // namespace y3

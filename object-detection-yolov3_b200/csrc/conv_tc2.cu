@@ -57,7 +57,7 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     using C = Conv2Cfg<BN2, NSTG_>;
     constexpr int BK = C::BK;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* smem = align_smem_1024(smem_raw);
     unsigned char* stage_base = smem;
     unsigned char* stg_base = smem + C::STAGES * C::STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + C::NSTG * C::STG_BYTES);

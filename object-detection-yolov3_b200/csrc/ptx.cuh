@@ -67,6 +67,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #endif
     return ok != 0;
 }
+// First 1024-byte aligned address of the dynamic shared memory.  Plain pointer arithmetic on the __shared__ array (not a
+// round trip through uintptr_t): the compiler keeps the address space, so every access through the result is an
+// LDS / STS instead of a generic LD / ST (which it also has to order against every other generic access).
+__device__ __forceinline__ unsigned char* align_smem_1024(unsigned char* smem_raw) {
+    return smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+}
 // Bounded wait: a broken pipeline traps (launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
