@@ -42,6 +42,16 @@ struct Conv2hCfg {
 
 struct TileCoord { int n0, x0, y0, img, mt; };
 
+#ifdef Y3_CONV_TRACE
+// measurement build only: where CTA 0's MMA thread, producer and first epilogue warp spend their cycles
+__device__ long long g_conv_trace[16];
+#define CT_BEGIN(v) const long long v = clock64()
+#define CT_ADD(slot, v) do { if (blockIdx.x == 0) g_conv_trace[slot] += clock64() - (v); } while (0)
+#else
+#define CT_BEGIN(v) do { } while (0)
+#define CT_ADD(slot, v) do { } while (0)
+#endif
+
 __device__ __forceinline__ TileCoord tile_coord(const ConvArgs& P, int t, int rank, int bn2) {
     TileCoord c;
     const int nt = t % P.n_tiles_n;
@@ -139,7 +149,9 @@ k_conv_tc2h(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     const int kh = tap / P.kwn;
                     const int kw = tap - kh * P.kwn;
                     for (int kc = 0; kc < P.kchunks; ++kc) {
+                        CT_BEGIN(c0);
                         mbar_wait(&empty[stage], phase ^ 1u);
+                        CT_ADD(0, c0);
                         unsigned char* sa = stage_base + stage * C::STAGE_BYTES;
                         const uint32_t lead_full = mapa_u32(&full[stage], 0);
                         if (rank == 0) mbar_expect_tx(&full[stage], (uint32_t)(2 * (rows * BK * 2 + C::B_BYTES)));
@@ -169,17 +181,22 @@ k_conv_tc2h(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
+            CT_BEGIN(c_all);
             for (int t = pair; t < total_pt; t += n_pairs, ++it) {
                 const int p = it & 1;
                 const uint32_t use = (uint32_t)(it >> 1);
+                CT_BEGIN(c1);
                 mbar_wait(&tmem_empty[p], (use & 1u) ^ 1u);
+                CT_ADD(1, c1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(p * BN2);
                 int kc = 0;
                 for (int ki = 0; ki < k_iters; ++ki) {
                     const uint32_t idesc = kc < P.k_split ? idesc1 : idesc2;
                     if (++kc == P.kchunks) kc = 0;
+                    CT_BEGIN(c2);
                     mbar_wait(&full[stage], phase);
+                    CT_ADD(2, c2);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(stage_base + stage * C::STAGE_BYTES);
                     const uint64_t adesc = make_smem_desc(a_addr, C::SBO, SWZ_128B);
@@ -192,6 +209,10 @@ k_conv_tc2h(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
+            CT_ADD(3, c_all);
+#ifdef Y3_CONV_TRACE
+            if (blockIdx.x == 0) g_conv_trace[4] += it;
+#endif
         }
     } else if (warp == 10) {
         // ------------------------------------------------------------ staging manager (each CTA, one thread)
@@ -250,7 +271,10 @@ k_conv_tc2h(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             const TileCoord c = tile_coord(P, t, (int)rank, BN2);
             const int p = it & 1;
             const uint32_t use = (uint32_t)(it >> 1);
+            CT_BEGIN(c5);
             mbar_wait(&tmem_full[p], use & 1u);
+            if (warp == 2 && lane == 0) CT_ADD(5, c5);
+            CT_BEGIN(c6);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * BN2);
             const bool pix_ok = (c.mt < m_tiles) && (row < rows) && (c.y0 + by < P.Ho) && (c.x0 + bx < P.Wo);
@@ -258,10 +282,12 @@ k_conv_tc2h(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 const int buf = hc & 1;
                 const uint32_t huse = (uint32_t)(hc >> 1);
                 unsigned char* stg = hs_base + buf * C::HS_BYTES;
+                CT_BEGIN(c7);
                 if (!P.out_f32) {
                     if (P.has_res) mbar_wait(&res_full[buf], huse & 1u);          // residual landed => buffer is ours
                     else if (hc >= 2) mbar_wait(&buf_free[buf], (huse & 1u) ^ 1u); // store of half hc-2 drained
                 }
+                if (warp == 2 && lane == 0) CT_ADD(7, c7);
 #pragma unroll 1
                 for (int g2 = gsel; g2 < 4; g2 += 2) {
                     const int g = h * 4 + g2;
@@ -322,6 +348,7 @@ k_conv_tc2h(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[p], 0));
+                    if (warp == 2 && lane == 0) CT_ADD(6, c6);
                 }
                 if (!P.out_f32) {
                     fence_proxy_async_smem();      // generic-proxy writes -> visible to the TMA store
@@ -348,8 +375,19 @@ static void launch2h_t(y3_context* ctx, const ConvLaunch& L) {
         Y3_CUDA(cudaFuncSetAttribute(k_conv_tc2h<BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr[ctx->device & 63] = true;
     }
+#ifdef Y3_CONV_TRACE
+    long long zero[16] = {};
+    cudaMemcpyToSymbol(g_conv_trace, zero, sizeof(zero));
+#endif
     launch_pdl(k_conv_tc2h<BN2>, L.grid, CONV2H_THREADS, C::SMEM, ctx->stream, L.map_a, L.map_a2, L.map_b, L.map_out, L.map_res, L.args);
     Y3_LAUNCHED(ctx);
+#ifdef Y3_CONV_TRACE
+    long long tr[16];
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpyFromSymbol(tr, g_conv_trace, sizeof(tr));
+    fprintf(stderr, "CONVTRACE cin %d taps %d kchunks %d ntn %d tiles %lld: mma total %lld = wait_tmem_empty %lld + wait_full %lld + issue %lld | producer wait_empty %lld | epi wait_tmem_full %lld, hold_acc %lld (of which wait_buffer %lld)\n",
+            L.args.cin, L.args.taps, L.args.kchunks, L.args.n_tiles_n, tr[4], tr[3], tr[1], tr[2], tr[3] - tr[1] - tr[2], tr[0], tr[5], tr[6], tr[7]);
+#endif
 }
 
 bool launch_conv2h(y3_context* ctx, const ConvLaunch& L) {

@@ -48,7 +48,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
 #if Y3_MBAR_SUSPEND_NS > 0
     // suspend-time hint: the waiting thread sleeps in hardware until the phase completes (or the hint expires)
-    // instead of re-issuing the poll - fewer wasted issue slots while the step is power-capped
+    // instead of re-issuing the poll - fewer wasted issue slots while the step is power-capped.  Also measured for the
+    // single MMA issuer thread alone (round 2): a pure poll on the operand-ring barriers makes the long 3x3 layers
+    // 3-5 % SLOWER (0.266 vs 0.259 ms at 128->256 @64^2) - the polls compete with the TMA's complete_tx updates.
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
