@@ -266,15 +266,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                     const int piece0 = (cc - ch * C::OC) >> 3;
                     unsigned char* rowp = stg + ch * C::CHUNK_BYTES + row * C::OCB;
                     const int sw = (C::OCB == 128) ? (row & 7) : ((row >> 1) & 3);
+                    if (P.has_res) {                     // block input: all four pieces requested first, one round trip
+#pragma unroll
+                        for (int pc = 0; pc < 4; ++pc) {
+                            const uint4 x = lds128(rowp + (((piece0 + pc) ^ sw) << 4));
+                            float* yy = y + pc * 8;
+                            yy[0] += bf16lo(x.x); yy[1] += bf16hi(x.x); yy[2] += bf16lo(x.y); yy[3] += bf16hi(x.y);
+                            yy[4] += bf16lo(x.z); yy[5] += bf16hi(x.z); yy[6] += bf16lo(x.w); yy[7] += bf16hi(x.w);
+                        }
+                    }
 #pragma unroll
                     for (int pc = 0; pc < 4; ++pc) {
                         uint4* dst = reinterpret_cast<uint4*>(rowp + (((piece0 + pc) ^ sw) << 4));
                         float* yy = y + pc * 8;
-                        if (P.has_res) {
-                            const uint4 x = *dst;
-                            yy[0] += bf16lo(x.x); yy[1] += bf16hi(x.x); yy[2] += bf16lo(x.y); yy[3] += bf16hi(x.y);
-                            yy[4] += bf16lo(x.z); yy[5] += bf16hi(x.z); yy[6] += bf16lo(x.w); yy[7] += bf16hi(x.w);
-                        }
                         uint4 o;
                         o.x = pack_act2(yy[0], yy[1], P.out_f16); o.y = pack_act2(yy[2], yy[3], P.out_f16);
                         o.z = pack_act2(yy[4], yy[5], P.out_f16); o.w = pack_act2(yy[6], yy[7], P.out_f16);

@@ -265,17 +265,21 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                     const int piece0 = (g & 1) * 4;
                     unsigned char* rowp = stg + ch * C::CHUNK_BYTES + row * 128;
                     const int sw = row & 7;
+                    if (P.has_res) {                     // block input: all four pieces requested first, one round trip
 #pragma unroll
-                    for (int pc = 0; pc < 4; ++pc) {
-                        uint4* dst = reinterpret_cast<uint4*>(rowp + (((piece0 + pc) ^ sw) << 4));
-                        float* yy = y + pc * 8;
-                        if (P.has_res) {
-                            const uint4 x = *dst;
+                        for (int pc = 0; pc < 4; ++pc) {
+                            const uint4 x = lds128(rowp + (((piece0 + pc) ^ sw) << 4));
+                            float* yy = y + pc * 8;
                             yy[0] += __uint_as_float(x.x << 16); yy[1] += __uint_as_float(x.x & 0xffff0000u);
                             yy[2] += __uint_as_float(x.y << 16); yy[3] += __uint_as_float(x.y & 0xffff0000u);
                             yy[4] += __uint_as_float(x.z << 16); yy[5] += __uint_as_float(x.z & 0xffff0000u);
                             yy[6] += __uint_as_float(x.w << 16); yy[7] += __uint_as_float(x.w & 0xffff0000u);
                         }
+                    }
+#pragma unroll
+                    for (int pc = 0; pc < 4; ++pc) {
+                        uint4* dst = reinterpret_cast<uint4*>(rowp + (((piece0 + pc) ^ sw) << 4));
+                        float* yy = y + pc * 8;
                         uint4 o;
                         o.x = pack_act2(yy[0], yy[1], P.out_f16); o.y = pack_act2(yy[2], yy[3], P.out_f16);
                         o.z = pack_act2(yy[4], yy[5], P.out_f16); o.w = pack_act2(yy[6], yy[7], P.out_f16);

@@ -75,6 +75,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ unsigned char* align_smem_1024(unsigned char* smem_raw) {
     return smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 }
+// 16-byte shared-memory load the compiler cannot speculate: inside `if (has_res)` it stays inside (a plain LDS gets
+// if-converted into an unconditional load + select, which puts an LDS round trip in front of every staging store of
+// the layers WITHOUT a residual: +8 % on conv2d_2).
+__device__ __forceinline__ uint4 lds128(const void* p) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
 // Bounded wait: a broken pipeline traps (launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
