@@ -1,5 +1,6 @@
 // conv_tc.cuh - host-side description of one tcgen05 implicit-GEMM convolution launch.
 #pragma once
+#include "ptx.cuh"
 #include <cuda.h>
 #include "common.cuh"
 #include <stdlib.h>
@@ -74,6 +75,33 @@ void launch_conv_halo(y3_context* ctx, const ConvLaunch& L);
 void launch_stem_conv1(y3_context* ctx, const ConvLaunch& L, const float* in, const float* stem_w_host, const float* stem_bias_host,
                        const float* stem_scale_host, const float* stem_shift_host, int H, int W);
 bool halo_supported(int cin, int cout_pad);
+
+// One 32-channel group of a conv epilogue: y = BN(LeakyReLU_0.2(acc + bias)), or acc + bias for a linear layer
+// (reference model.py:29-39: Conv2D bias -> LeakyReLU(0.2) -> BatchNorm folded to scale/shift), in packed f32x2
+// arithmetic.  LINEAR is a template argument so that the layer kind is one branch per group instead of a predicate
+// on every element (the if-converted form cost ~7 instructions per value, this one ~2.5).
+// b / s / t = the group's 32 bias / scale / shift values in global memory (16-byte aligned, read-only path).
+template <bool LINEAR>
+__device__ __forceinline__ void epilogue_math_32(const uint32_t (&v)[32], const float* __restrict__ b, const float* __restrict__ s,
+                                                 const float* __restrict__ t, float (&y)[32]) {
+    using namespace ptx;
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(b) + k4);
+        float2 za = add2_f32(make_float2(__uint_as_float(v[4 * k4 + 0]), __uint_as_float(v[4 * k4 + 1])), make_float2(b4.x, b4.y));
+        float2 zb = add2_f32(make_float2(__uint_as_float(v[4 * k4 + 2]), __uint_as_float(v[4 * k4 + 3])), make_float2(b4.z, b4.w));
+        if (!LINEAR) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(s) + k4);
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(t) + k4);
+            float2 la = mul2_f32(za, make_float2(0.2f, 0.2f)), lb = mul2_f32(zb, make_float2(0.2f, 0.2f));
+            la.x = fmaxf(la.x, za.x); la.y = fmaxf(la.y, za.y);        // leaky(z) = max(z, 0.2 z)
+            lb.x = fmaxf(lb.x, zb.x); lb.y = fmaxf(lb.y, zb.y);
+            za = fma2_f32(la, make_float2(s4.x, s4.y), make_float2(t4.x, t4.y));
+            zb = fma2_f32(lb, make_float2(s4.z, s4.w), make_float2(t4.z, t4.w));
+        }
+        y[4 * k4 + 0] = za.x; y[4 * k4 + 1] = za.y; y[4 * k4 + 2] = zb.x; y[4 * k4 + 3] = zb.y;
+    }
+}
 
 }  // namespace y3
 

@@ -296,23 +296,8 @@ k_conv_tc2h(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     tmem_ld_wait();
                     const int c0 = c.n0 + g * 32;
                     float y[32];
-#pragma unroll
-                    for (int k4 = 0; k4 < 8; ++k4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.bias + c0) + k4);
-                        float z0 = __uint_as_float(v[4 * k4 + 0]) + b4.x;
-                        float z1 = __uint_as_float(v[4 * k4 + 1]) + b4.y;
-                        float z2 = __uint_as_float(v[4 * k4 + 2]) + b4.z;
-                        float z3 = __uint_as_float(v[4 * k4 + 3]) + b4.w;
-                        if (!P.linear) {
-                            const float4 s4 = __ldg(reinterpret_cast<const float4*>(P.scale + c0) + k4);
-                            const float4 t4 = __ldg(reinterpret_cast<const float4*>(P.shift + c0) + k4);
-                            z0 = (z0 > 0.f ? z0 : 0.2f * z0) * s4.x + t4.x;
-                            z1 = (z1 > 0.f ? z1 : 0.2f * z1) * s4.y + t4.y;
-                            z2 = (z2 > 0.f ? z2 : 0.2f * z2) * s4.z + t4.z;
-                            z3 = (z3 > 0.f ? z3 : 0.2f * z3) * s4.w + t4.w;
-                        }
-                        y[4 * k4 + 0] = z0; y[4 * k4 + 1] = z1; y[4 * k4 + 2] = z2; y[4 * k4 + 3] = z3;
-                    }
+                    if (P.linear) epilogue_math_32<true>(v, P.bias + c0, P.scale + c0, P.shift + c0, y);
+                    else epilogue_math_32<false>(v, P.bias + c0, P.scale + c0, P.shift + c0, y);
                     if (P.out_f32) {
                         if (pix_ok) {
                             const long long pix = ((long long)c.img * P.Ho + (c.y0 + by)) * P.Wo + (c.x0 + bx);
