@@ -76,6 +76,21 @@ void launch_stem_conv1(y3_context* ctx, const ConvLaunch& L, const float* in, co
                        const float* stem_scale_host, const float* stem_shift_host, int H, int W);
 bool halo_supported(int cin, int cout_pad);
 
+// 32 epilogue values of one pixel -> four 16-byte pieces of its (swizzled) staging row: piece pc goes to
+// rowp + (((piece0 + pc) ^ sw) << 4).  F16 = the tensor is stored as fp16 (saturating) instead of bf16; a template
+// argument so that only one of the two conversions is emitted per group.
+template <bool F16>
+__device__ __forceinline__ void stage_row_32(const float (&y)[32], unsigned char* rowp, int piece0, int sw) {
+#pragma unroll
+    for (int pc = 0; pc < 4; ++pc) {
+        const float* yy = y + pc * 8;
+        uint4 o;
+        o.x = ptx::pack_act2(yy[0], yy[1], F16); o.y = ptx::pack_act2(yy[2], yy[3], F16);
+        o.z = ptx::pack_act2(yy[4], yy[5], F16); o.w = ptx::pack_act2(yy[6], yy[7], F16);
+        *reinterpret_cast<uint4*>(rowp + (((piece0 + pc) ^ sw) << 4)) = o;
+    }
+}
+
 // One 32-channel group of a conv epilogue: y = BN(LeakyReLU_0.2(acc + bias)), or acc + bias for a linear layer
 // (reference model.py:29-39: Conv2D bias -> LeakyReLU(0.2) -> BatchNorm folded to scale/shift), in packed f32x2
 // arithmetic.  LINEAR is a template argument so that the layer kind is one branch per group instead of a predicate

@@ -261,15 +261,8 @@ k_conv_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                             yy[6] += __uint_as_float(x.w << 16); yy[7] += __uint_as_float(x.w & 0xffff0000u);
                         }
                     }
-#pragma unroll
-                    for (int pc = 0; pc < 4; ++pc) {
-                        uint4* dst = reinterpret_cast<uint4*>(rowp + (((piece0 + pc) ^ sw) << 4));
-                        float* yy = y + pc * 8;
-                        uint4 o;
-                        o.x = pack_act2(yy[0], yy[1], P.out_f16); o.y = pack_act2(yy[2], yy[3], P.out_f16);
-                        o.z = pack_act2(yy[4], yy[5], P.out_f16); o.w = pack_act2(yy[6], yy[7], P.out_f16);
-                        *dst = o;
-                    }
+                    if (P.out_f16) stage_row_32<true>(y, rowp, piece0, sw);
+                    else stage_row_32<false>(y, rowp, piece0, sw);
                 }
             }
             // accumulator drained: release it to the leader's MMA thread (remote arrive from rank 1)
