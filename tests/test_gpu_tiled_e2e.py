@@ -250,3 +250,29 @@ def test_tiled_end_to_end_vs_fp32_oracle_network():
         if bound is not None:
             assert min(px1, px2, iou1, iou2) >= bound, report
     print("\n".join(report))
+
+
+def test_result_rows_are_owned_by_the_caller():
+    """the host results come out of recycled page-locked blocks (engine._result_rows): results kept alive must
+    not be overwritten by later calls, blocks of dropped results are reused, and hoarders get pageable arrays"""
+    from yolo3_b200 import engine as eng_mod
+    img = cases.synthetic_image(520, 600, 1, np.uint16, seed=3, blobs=20)
+    eng = standardised_engine(img, 64, 4)
+    first = eng.infer_tiled(img, TILE, 24, edge_range=64)
+    want = first.copy()
+    assert want.shape[0] > 10
+    img2 = np.ascontiguousarray(img[::-1])                       # a different image: different rows
+    kept = [eng.infer_tiled(img2 if i % 2 else img, TILE, 24, edge_range=64) for i in range(eng_mod._LEASES_MAX + 3)]
+    assert np.array_equal(first, want)
+    for i, r in enumerate(kept):
+        assert np.array_equal(r, kept[i % 2]) and (i % 2 == 0) == np.array_equal(r, want)
+    ptrs = {r.ctypes.data for r in kept} | {first.ctypes.data}
+    assert len(ptrs) == len(kept) + 1                            # no two live results share memory
+    state = next(iter(eng._row_pool.values()))
+    assert state["out"] == eng_mod._LEASES_MAX                   # the rest are pageable
+    del kept, first, r
+    import gc
+    gc.collect()
+    assert state["out"] == 0 and len(state["free"]) == eng_mod._LEASES_MAX
+    again = eng.infer_tiled(img, TILE, 24, edge_range=64)
+    assert np.array_equal(again, want) and len(state["free"]) == eng_mod._LEASES_MAX - 1
