@@ -380,7 +380,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--image-side", type=int, default=20000)
     ap.add_argument("--edge", type=int, default=64, help="EDGE_EFFECT_RANGE; 64 = BASELINE wording, 96 = reference constant")
-    ap.add_argument("--batch", type=int, default=0, help="tiles per forward batch (0 = auto: <= 256, at least 3 batches per rank)")
+    ap.add_argument("--batch", type=int, default=0, help="largest tile batch of the engine (0 = 256, the facade's BATCH_SIZE)")
     ap.add_argument("--cpu-sample-tiles", type=int, default=96)
     args = ap.parse_args()
 
@@ -446,10 +446,10 @@ def main():
     n_tiles = tile_count(side, side, TILE, edge)
     first, count = shard_range(n_tiles, rank, world)
     if args.batch <= 0:
-        # measured on one B200 (power-capped step): 64 -> 1164, 128 -> 1224, 192 -> 1244, 256 -> 1252, 384 -> 1247 Mpix/s;
-        # keep at least 3 batches per rank so that post-processing of batch k overlaps the convolutions of batch k+1
-        n_batches = max(3, -(-count // 256))
-        args.batch = max(1, -(-count // n_batches))
+        # the facade's BATCH_SIZE (inference_tiled.py); the library splits a call's tiles evenly into at least three
+        # batches of at most this many tiles.  Measured on one B200 (power-capped step): 64 -> 1164, 128 -> 1224,
+        # 192 -> 1244, 256 -> 1252, 384 -> 1247 Mpix/s
+        args.batch = min(256, max(1, count))
     cfg.update(tiles=n_tiles, tiles_this_rank=count, tile_batch=args.batch, parallelism="tile-sharded x%d" % world)
 
     eng = Engine(TILE + (1,), NC, ANCHORS, max_batch=args.batch, device=local)

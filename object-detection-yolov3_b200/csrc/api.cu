@@ -699,19 +699,28 @@ void infer_tiled_impl(y3_handle h, const void* img, y3_dtype dt, y3_mem img_mem,
         BandUpload U = begin_band_upload(h, T, img, dt, img_mem, W, C, geo, tile_first, tile_count);
         const void* d_img = U.dev;
         const long long row_lo = U.row_lo;
-        // tiles of the batch that starts at t0.  With the image in host memory the first batch is short, so that the
-        // convolutions start after a small upload and the rest of the band streams in behind them.
-        auto batch_tiles = [&](int64_t t0) {
-            const int64_t full = (U.host && t0 == 0) ? std::min<int64_t>(net->maxB, 48) : net->maxB;
-            return (int)std::min<int64_t>(full, tile_count - t0);
-        };
-        auto rows_needed = [&](int64_t t0) {                  // last image row (exclusive) batch t0 reads
+        // Batch plan.  With the image in host memory the first batch is short (at most one row of tiles is worth waiting
+        // for: the convolutions start after a small upload and the rest of the band streams in behind them).  The
+        // remaining tiles are split EVENLY into as few batches as fit the network's capacity, but into at least three
+        // batches per call (post-processing of batch k overlaps the convolutions of batch k+1; the last batch's
+        // post-processing is exposed) unless that would make them smaller than 32 tiles.
+        std::vector<int> plan;
+        {
+            int64_t left = tile_count;
+            if (U.host) { plan.push_back((int)std::min<int64_t>({(int64_t)net->maxB, 48, left})); left -= plan.back(); }
+            if (left > 0) {
+                int64_t nb = (left + net->maxB - 1) / net->maxB;
+                const int64_t want = 3 - (int64_t)plan.size();
+                if (nb < want) nb = std::max(nb, std::min<int64_t>(want, left / 32));
+                for (int64_t i = 0; i < nb; ++i) plan.push_back((int)(left / nb + (i < left % nb ? 1 : 0)));
+            }
+        }
+        auto rows_needed = [&](int64_t t0, int n) {           // last image row (exclusive) the batch [t0, t0 + n) reads
             int need = 0;
-            const int64_t n = batch_tiles(t0);
             for (int64_t t = 0; t < n; ++t) need = std::max(need, geo[tile_first + t0 + t].y1);
             return need;
         };
-        cudaEvent_t ready = upload_rows_until(h, U, rows_needed(0));
+        cudaEvent_t ready = upload_rows_until(h, U, rows_needed(0, plan[0]));
         StitchArgs S{H, W, th, tw, edge};
         const int B = net->maxB;
         const bool seg = PostProc::segmented_ok(heads_source(net, 1, true, min_box, score_thr)) && !getenv("Y3_NMS_GLOBAL_SORT");
@@ -751,15 +760,16 @@ void infer_tiled_impl(y3_handle h, const void* img, y3_dtype dt, y3_mem img_mem,
         };
         int64_t prev_t0 = -1; int prev_nb = 0, prev_set = 0; cudaEvent_t prev_ev = nullptr;
         int it = 0;
-        for (int64_t t0 = 0; t0 < tile_count; t0 += batch_tiles(t0), ++it) {
-            const int nb = batch_tiles(t0);
+        int64_t t0 = 0;
+        for (size_t bi = 0; bi < plan.size(); t0 += plan[bi], ++bi, ++it) {
+            const int nb = plan[bi];
             const TileGeo* g = d_geo + tile_first + t0;
             const int set = it & 1;
             {   // wait for this batch's rows, then start the next batch's upload so it overlaps this batch's compute
                 Phase p(h, &Tm.ms_h2d, "y3:h2d");
                 if (ready) Y3_CUDA(cudaStreamWaitEvent(h->stream, ready, 0));
                 p.stop();
-                if (t0 + nb < tile_count) ready = upload_rows_until(h, U, rows_needed(t0 + nb));
+                if (bi + 1 < plan.size()) ready = upload_rows_until(h, U, rows_needed(t0 + nb, plan[bi + 1]));
             }
             { Phase p(h, &Tm.ms_prep, "y3:tile_slice_zscore"); launch_tile_norm(h, d_img, dt, row_lo, (int)W, C, g, nb, th, tw, T->tiles.as<float>(), nullptr, T->sums.as<double>()); p.stop(); }
             { Phase p(h, &Tm.ms_conv, "y3:conv_stack"); net->forward(T->tiles.as<float>(), nb, set); p.stop(); }
