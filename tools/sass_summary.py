@@ -13,7 +13,8 @@ txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True,
 classes = [("UTCHMMA.2CTA", r"\bUTCHMMA\.2CTA"), ("UTCHMMA", r"\bUTCHMMA\b(?!\.2CTA)"), ("UTMALDG.IM2COL", r"\bUTMALDG\.\dD\.IM2COL"),
            ("UTMALDG", r"\bUTMALDG\b"), ("UTMASTG", r"\bUTMASTG\b"), ("LDTM", r"\bLDTM\b"), ("UTCBAR", r"\bUTCBAR\b"),
            ("SYNCS", r"\bSYNCS\b"), ("REDUX", r"\bREDUX\b"), ("MATCH", r"\bMATCH\b"), ("ATOM/RED", r"\b(ATOMG|ATOMS|ATOM|RED)\b"),
-           ("FFMA2/FMUL2", r"\b(FFMA2|FMUL2|FADD2)\b"), ("HMMA", r"\bHMMA\b"), ("LDG", r"\bLDG\b"), ("STG", r"\bSTG\b"), ("MUFU", r"\bMUFU\b")]
+           ("FFMA2/FMUL2", r"\b(FFMA2|FMUL2|FADD2)\b"), ("HMMA", r"\bHMMA\b"), ("LDG", r"\bLDG\b"), ("STG", r"\bSTG\b"),
+           ("LDS", r"\bLDS\b"), ("STS", r"\bSTS\b"), ("generic LD/ST", r"\b(LD|ST)\.E\b"), ("LDL/STL", r"\b(LDL|STL)\b"), ("MUFU", r"\bMUFU\b")]
 cur, rows, counts, total = None, [], None, 0
 for line in txt.splitlines():
     m = re.search(r"Function : (\S+)", line)
