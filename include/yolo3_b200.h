@@ -55,7 +55,8 @@ typedef struct {
     int32_t num_classes;
     int32_t num_anchors;            /* ALL anchors are used at every scale (model.py:108-111) */
     float anchors[Y3_MAX_ANCHORS][2]; /* (w, h) pixels; default (32,32),(128,128),(256,256) model.py:433 */
-    int32_t max_batch;              /* images (tiles) per forward launch sequence */
+    int32_t max_batch;              /* largest number of images (tiles) per forward launch sequence; the tiled entry
+                                     * points split a call's tiles evenly into batches of at most this many */
     int32_t device;                 /* CUDA ordinal (the reference uses CUDA_VISIBLE_DEVICES) */
     int64_t max_candidates;         /* capacity of the (box,class) candidate list; 0 = default */
 } y3_config;
@@ -190,7 +191,9 @@ y3_status y3_stitch_tiles(y3_handle h, const float* dets, y3_mem dets_mem, int64
 /* replaces: inference_tiled.inference_image_tiled (inference_tiled.py:185-310) for tiles
  * [tile_first, tile_first+tile_count) (tile_count < 0 = to the end) - the unit that is sharded
  * across GPUs.  img is the WHOLE HWC image (host|device); only the rows the tile range needs are
- * copied to the device.  preds as in y3_stitch_tiles. */
+ * copied to the device (band by band on a copy stream, behind a short first batch, when the image is in
+ * page-locked host memory).  The result does not depend on how the tiles are batched.  preds as in
+ * y3_stitch_tiles; a host preds buffer is best page-locked (y3_host_alloc). */
 y3_status y3_infer_tiled(y3_handle h, const void* img, y3_dtype dtype, y3_mem img_mem,
                          int64_t img_h, int64_t img_w, int32_t img_c,
                          int32_t tile_h, int32_t tile_w, int32_t edge_range,

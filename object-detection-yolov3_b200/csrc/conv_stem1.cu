@@ -68,20 +68,6 @@ __device__ __forceinline__ uint32_t pack2s(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
-// acquire at cluster scope: the waited-for data was written through the generic proxy by warps of BOTH CTAs
-__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0, ok = 0;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred P;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, P;\n\t}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(10000u)
-            : "memory");
-        if (!ok && ++spins > (1u << 18)) { printf("y3: stem ring timeout block %d\n", blockIdx.x); __trap(); }
-    } while (!ok);
-}
 __device__ __forceinline__ uint64_t make_smem_desc_interleaved(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
