@@ -155,6 +155,9 @@ k_conv_tc2h(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         unsigned char* sa = stage_base + stage * C::STAGE_BYTES;
                         const uint32_t lead_full = mapa_u32(&full[stage], 0);
                         if (rank == 0) mbar_expect_tx(&full[stage], (uint32_t)(2 * (rows * BK * 2 + C::B_BYTES)));
+                        // weights first: every pair asks for the same slice at about the same time (the L2 merges those
+                        // requests); measured -1.6 % on the 128->256 @64^2 class against activations-first
+                        tma2_load_2d(sa + C::A_BYTES, &map_b, lead_full, tap * P.cin + kc * BK, c.n0 + (int)rank * (BN2 / 2));
                         if (P.im2col) {
                             tma2_load_im2col_4d(sa, &map_a, lead_full, kc * BK, im_w, im_h, im_n, (uint16_t)kw, (uint16_t)kh);
                         } else if (P.stride == 1) {
@@ -163,7 +166,6 @@ k_conv_tc2h(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         } else {
                             tma2_load_5d(sa, &map_a, lead_full, (kw & 1) * P.a_cpitch + kc * BK, c.x0 + (kw >> 1), kh & 1, c.y0 + (kh >> 1), c.img);
                         }
-                        tma2_load_2d(sa + C::A_BYTES, &map_b, lead_full, tap * P.cin + kc * BK, c.n0 + (int)rank * (BN2 / 2));
                         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                     }
                 }
