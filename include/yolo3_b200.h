@@ -157,6 +157,14 @@ y3_status y3_per_class_nms(y3_handle h, const float* boxes /*[n,4]*/, const floa
 int64_t y3_tile_plan(int64_t img_h, int64_t img_w, int32_t tile_h, int32_t tile_w, int32_t edge_range,
                      int32_t* xs, int32_t* ys, int64_t cap);
 
+/* How y3_infer_tiled / y3_infer_tiled_sharded batch `tile_count` tiles on a handle created with `max_batch`
+ * (no reference counterpart: the reference runs one tile per model call, inference_tiled.py:213-216).  With the image
+ * in host memory the first batch is short (<= 48 tiles: the convolutions start after one row of tiles has been
+ * uploaded); the other tiles are split evenly into as few batches as max_batch allows, but into at least three
+ * batches per call unless that would make them smaller than 32 tiles.  Returns the number of batches; sizes
+ * (optional, capacity cap) receives their tile counts.  Host-only, needs no handle. */
+int64_t y3_batch_plan(int64_t tile_count, int32_t max_batch, int32_t host_image, int32_t* sizes, int64_t cap);
+
 /* replaces: inference_tiled.convert_image_to_tiles pixels (inference_tiled.py:29-100): the raw tiles
  * [first, first+count) in the SOURCE dtype, HWC each: out [count, tile_h, tile_w, C] (host|device). */
 y3_status y3_tiles_raw(y3_handle h, const void* img, y3_dtype dtype, y3_mem img_mem,

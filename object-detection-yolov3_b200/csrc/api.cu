@@ -37,6 +37,20 @@ static thread_local std::string g_create_error;
     }
 
 namespace {
+// Sizes of the tile batches of one tiled call (see the comment in infer_tiled_impl; exported as y3_batch_plan).
+std::vector<int> batch_plan(int64_t tile_count, int64_t max_batch, bool host_image) {
+    std::vector<int> plan;
+    int64_t left = tile_count;
+    if (host_image && left > 0) { plan.push_back((int)std::min<int64_t>({max_batch, 48, left})); left -= plan.back(); }
+    if (left > 0) {
+        int64_t nb = (left + max_batch - 1) / max_batch;
+        const int64_t want = 3 - (int64_t)plan.size();
+        if (nb < want) nb = std::max(nb, std::min<int64_t>(want, left / 32));
+        for (int64_t i = 0; i < nb; ++i) plan.push_back((int)(left / nb + (i < left % nb ? 1 : 0)));
+    }
+    return plan;
+}
+
 
 const void* to_device(y3_context* c, const void* p, y3_mem mem, size_t bytes, DevBuf& stage) {
     if (mem == Y3_MEM_DEVICE) return p;
@@ -462,6 +476,14 @@ int64_t y3_tile_plan(int64_t img_h, int64_t img_w, int32_t tile_h, int32_t tile_
     }
 }
 
+int64_t y3_batch_plan(int64_t tile_count, int32_t max_batch, int32_t host_image, int32_t* sizes, int64_t cap) {
+    if (tile_count < 0 || max_batch < 1) { g_create_error = "y3_batch_plan: bad arguments"; return Y3_ERR_INVALID; }
+    const std::vector<int> v = batch_plan(tile_count, max_batch, host_image != 0);
+    for (size_t i = 0; i < v.size() && (int64_t)i < cap; ++i)
+        if (sizes) sizes[i] = v[i];
+    return (int64_t)v.size();
+}
+
 namespace {
 // uploads the rows of the image that tiles [first, first+count) touch; returns the device pointer and row_lo
 const void* upload_band(y3_context* h, Tiler* T, const void* img, y3_dtype dt, y3_mem mem, int64_t W, int C,
@@ -704,17 +726,7 @@ void infer_tiled_impl(y3_handle h, const void* img, y3_dtype dt, y3_mem img_mem,
         // remaining tiles are split EVENLY into as few batches as fit the network's capacity, but into at least three
         // batches per call (post-processing of batch k overlaps the convolutions of batch k+1; the last batch's
         // post-processing is exposed) unless that would make them smaller than 32 tiles.
-        std::vector<int> plan;
-        {
-            int64_t left = tile_count;
-            if (U.host) { plan.push_back((int)std::min<int64_t>({(int64_t)net->maxB, 48, left})); left -= plan.back(); }
-            if (left > 0) {
-                int64_t nb = (left + net->maxB - 1) / net->maxB;
-                const int64_t want = 3 - (int64_t)plan.size();
-                if (nb < want) nb = std::max(nb, std::min<int64_t>(want, left / 32));
-                for (int64_t i = 0; i < nb; ++i) plan.push_back((int)(left / nb + (i < left % nb ? 1 : 0)));
-            }
-        }
+        const std::vector<int> plan = batch_plan(tile_count, net->maxB, U.host != nullptr);
         auto rows_needed = [&](int64_t t0, int n) {           // last image row (exclusive) the batch [t0, t0 + n) reads
             int need = 0;
             for (int64_t t = 0; t < n; ++t) need = std::max(need, geo[tile_first + t0 + t].y1);

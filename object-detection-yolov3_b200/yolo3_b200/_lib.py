@@ -52,6 +52,7 @@ PROTOTYPES = {
     "y3_per_class_nms": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_float,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_int64)]),
     "y3_tile_plan": (c_int64, [c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int64]),
+    "y3_batch_plan": (c_int64, [c_int64, c_int32, c_int32, c_void_p, c_int64]),
     "y3_tiles_normalized": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int64, c_int32, c_int32,
                                       c_int32, c_int32, c_int64, c_int64, c_void_p, c_int32]),
     "y3_zscore": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_void_p, c_int32]),

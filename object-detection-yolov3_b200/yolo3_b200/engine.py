@@ -435,6 +435,15 @@ def tile_plan(img_h, img_w, tile_size, edge_range):
     return xs, ys
 
 
+def batch_plan(tile_count, max_batch, host_image):
+    """tile counts of the batches y3_infer_tiled runs for tile_count tiles (y3_batch_plan; host-only)"""
+    sizes = np.empty(max(1, int(tile_count)), np.int32)
+    n = _lib.load().y3_batch_plan(int(tile_count), int(max_batch), 1 if host_image else 0, sizes.ctypes.data, sizes.size)
+    if n < 0:
+        raise ValueError("y3_batch_plan(%r, %r): bad arguments" % (tile_count, max_batch))
+    return sizes[:n].tolist()
+
+
 class _PinnedBlock:
     """One y3_host_alloc block, exposed through the array interface: numpy arrays made from it keep it alive
     (arr.base), and it is returned to CUDA when the last of them goes away."""

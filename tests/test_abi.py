@@ -54,3 +54,30 @@ def test_no_cpu_fallback():
     with pytest.raises(Y3Error) as e:
         Engine()
     assert e.value.code == -6 and "no CPU fallback" in str(e.value)
+
+
+def test_batch_plan_host_logic():
+    """y3_batch_plan: how the tiled entry points batch their tiles (pure host logic)"""
+    from yolo3_b200 import batch_plan
+    # the bench workload on 1 / 4 / 8 GPUs, image resident on the device and in host memory
+    assert batch_plan(2809, 256, False) == [256] * 4 + [255] * 7
+    assert batch_plan(352, 256, False) == [118, 117, 117]
+    assert batch_plan(352, 256, True) == [48, 152, 152]
+    assert batch_plan(703, 256, True) == [48, 219, 218, 218]
+    for count in (0, 1, 2, 31, 47, 48, 49, 95, 96, 97, 200, 352, 703, 2809, 3969):
+        for max_batch in (1, 4, 32, 118, 256):
+            for host in (False, True):
+                plan = batch_plan(count, max_batch, host)
+                assert sum(plan) == count and all(0 < b <= max_batch for b in plan), (count, max_batch, host, plan)
+                if count == 0:
+                    assert plan == []
+                    continue
+                rest = plan[1:] if host else plan
+                if host:
+                    assert plan[0] == min(48, max_batch, count)
+                if rest:
+                    assert max(rest) - min(rest) <= 1                                 # even split, no small tail batch
+                    assert len(rest) == max(-(-sum(rest) // max_batch), min(3 - (1 if host else 0), sum(rest) // 32), 1)
+    import pytest
+    with pytest.raises(ValueError):
+        batch_plan(10, 0, False)
