@@ -41,13 +41,14 @@ static constexpr int SC_STEM_WARPS = 8;
 static constexpr int SC_EPI_WARPS = 8;                    // two groups of 4: group e drains the tiles with (tile & 1) == e
 static constexpr int SC_THREADS = 64 + 32 * SC_EPI_WARPS + 32 * SC_STEM_WARPS + 32;   // + the 257th-column warp
 static constexpr int SC_FULL_ARRIVALS = 2 * (SC_STEM_WARPS + 1);
+static constexpr int SC_RING_SLOTS = 7;                   // ring slots (stem rows)
 
 struct SCfg {
     static constexpr int CIN = 32, COUT = 64, ROWB = 64;
     static constexpr int E_BYTES = 9216;                  // 129 rows x 64 B, padded to 1024
     static constexpr int O_BYTES = 8192;                  // 128 rows x 64 B
     static constexpr int SLOT = E_BYTES + O_BYTES;
-    static constexpr int S = 7;                           // ring slots (stem rows)
+    static constexpr int S = SC_RING_SLOTS;
     static constexpr int WTAP = (COUT / 2) * ROWB;        // this CTA's half of one conv2d_1 tap
     static constexpr int W_BYTES = 9 * WTAP;
     static constexpr int STG_BYTES = 128 * COUT * 2;
@@ -145,6 +146,7 @@ struct Steps {
     int t, h0, len, g;         // run: first tile, its row, tiles; position inside the run
     int ip, w0;                // run: image pair, first conv2d_1 output column
     int gs, k;                 // global step counter; ring row index of the step's first produced row
+    int slot, par;             // k % S and (k / S) & 1, kept incrementally (S = ring slots)
     __device__ __forceinline__ void start_run() {
         if (t < t_end) {
             const int col = t / Ho;
@@ -156,13 +158,16 @@ struct Steps {
         }
     }
     __device__ __forceinline__ void init(int t_begin, int t_end_, int Ho_, int tiles_x_) {
-        t_end = t_end_; Ho = Ho_; tiles_x = tiles_x_; t = t_begin; gs = 0; k = 0;
+        t_end = t_end_; Ho = Ho_; tiles_x = tiles_x_; t = t_begin; gs = 0; k = 0; slot = 0; par = 0;
         h0 = len = g = ip = w0 = 0;
         start_run();
     }
     __device__ __forceinline__ bool done() const { return t >= t_end; }
     __device__ __forceinline__ void next() {
-        k += g == 0 ? 1 : 2;
+        const int n = g == 0 ? 1 : 2;
+        k += n;
+        slot += n;
+        if (slot >= SC_RING_SLOTS) { slot -= SC_RING_SLOTS; par ^= 1; }
         ++gs;
         if (++g > len) { t += len; start_run(); }
     }
@@ -172,7 +177,8 @@ struct Steps {
 
 // what the stem warps remember about the step whose accumulators they still have to drain
 struct StepInfo {
-    int valid, buf, y0, w0, k, first;      // k = ring row index of the step's first produced row
+    int valid, buf, y0, w0, first;
+    int slot, par;                         // ring slot / use parity of the step's first produced row
     uint32_t use;
 };
 
@@ -350,16 +356,18 @@ k_stem_conv1(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ 
             const bool img_ok = img < P.n_img;
             const float* imgp = T.in + (long long)(img_ok ? img : 0) * H * W;
             const int first = st.first();
-            const int k_q0 = st.k, k_q1 = first ? st.k : st.k + 1;
-            if (!first) mbar_wait(&empty[k_q0 % C::S], (uint32_t)(((k_q0 / C::S) & 1) ^ 1));
-            mbar_wait(&empty[k_q1 % C::S], (uint32_t)(((k_q1 / C::S) & 1) ^ 1));
-            unsigned char* const re[2] = {ring + (k_q0 % C::S) * C::SLOT + 128 * C::ROWB, ring + (k_q1 % C::S) * C::SLOT + 128 * C::ROWB};
+            const int slot0 = st.slot, par0 = st.par;
+            int slot1 = slot0, par1 = par0;
+            if (!first && ++slot1 == C::S) { slot1 = 0; par1 ^= 1; }
+            if (!first) mbar_wait(&empty[slot0], (uint32_t)(par0 ^ 1));
+            mbar_wait(&empty[slot1], (uint32_t)(par1 ^ 1));
+            unsigned char* const re[2] = {ring + slot0 * C::SLOT + 128 * C::ROWB, ring + slot1 * C::SLOT + 128 * C::ROWB};
             stem_pixel_by_lanes(imgp, img_ok, H, W, st.y0(), 2 * st.w0 + 256, s_w, s_sp, lane, re, first != 0);
             fence_proxy_async_smem();              // generic-proxy writes -> visible to the tensor core's reads
             __syncwarp();
             if (lane == 0) {
-                if (!first) mbar_arrive_cluster(mapa_u32(&full[k_q0 % C::S], 0));
-                mbar_arrive_cluster(mapa_u32(&full[k_q1 % C::S], 0));
+                if (!first) mbar_arrive_cluster(mapa_u32(&full[slot0], 0));
+                mbar_arrive_cluster(mapa_u32(&full[slot1], 0));
             }
         }
     } else if (warp >= 2 + SC_EPI_WARPS) {
@@ -379,11 +387,13 @@ k_stem_conv1(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ 
             tc_fence_after();
             const bool mine = !(s.first && hi == 0);            // step 0 of a run: its first stem row is not needed
             const uint32_t t_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + C::STEM_COL0 + (uint32_t)(s.buf * 128 + hi * 64);
-            // ring rows of this step: [first ? nothing : row k] , row k + (first ? 0 : 1)
-            const int k_q0 = s.k, k_q1 = s.first ? s.k : s.k + 1;
-            if (!s.first) mbar_wait(&empty[k_q0 % C::S], (uint32_t)(((k_q0 / C::S) & 1) ^ 1));
-            mbar_wait(&empty[k_q1 % C::S], (uint32_t)(((k_q1 / C::S) & 1) ^ 1));
-            unsigned char* const slot_mine = ring + ((hi ? k_q1 : k_q0) % C::S) * C::SLOT;      // the ring row this warp writes
+            // ring rows of this step: [first ? nothing : the row in slot0] , the next row (first: slot0 itself)
+            const int slot0 = s.slot, par0 = s.par;
+            int slot1 = slot0, par1 = par0;
+            if (!s.first && ++slot1 == C::S) { slot1 = 0; par1 ^= 1; }
+            if (!s.first) mbar_wait(&empty[slot0], (uint32_t)(par0 ^ 1));
+            mbar_wait(&empty[slot1], (uint32_t)(par1 ^ 1));
+            unsigned char* const slot_mine = ring + (hi ? slot1 : slot0) * C::SLOT;      // the ring row this warp writes
             if (tr_on) TR(tr_role, gs_now, 3);
             if (mine) {
                 const int y = s.y0 + hi;
@@ -419,8 +429,8 @@ k_stem_conv1(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive_cluster(mapa_u32(&sacc_empty[s.buf], 0));
-                if (!s.first) mbar_arrive_cluster(mapa_u32(&full[k_q0 % C::S], 0));
-                mbar_arrive_cluster(mapa_u32(&full[k_q1 % C::S], 0));
+                if (!s.first) mbar_arrive_cluster(mapa_u32(&full[slot0], 0));
+                mbar_arrive_cluster(mapa_u32(&full[slot1], 0));
             }
             if (tr_on) TR(tr_role, gs_now, 7);
         };
@@ -442,7 +452,7 @@ k_stem_conv1(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ 
             const int buf = st.gs & 1;
             const uint32_t use = (uint32_t)(st.gs >> 1);
             StepInfo cur;
-            cur.valid = 1; cur.buf = buf; cur.use = use; cur.y0 = st.y0(); cur.w0 = st.w0; cur.k = st.k; cur.first = st.first();
+            cur.valid = 1; cur.buf = buf; cur.use = use; cur.y0 = st.y0(); cur.w0 = st.w0; cur.slot = st.slot; cur.par = st.par; cur.first = st.first();
             const int gs_now = st.gs;
             st.next();
             if (tr_on) TR(tr_role, gs_now, 0);
